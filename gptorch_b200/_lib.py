@@ -1,0 +1,122 @@
+"""ctypes binding of libgpb200.so (the C ABI declared in include/gpb200.h).
+
+This is the only place Python touches the native library.  Arguments are raw device pointers
+(``tensor.data_ptr()``), sizes, leading dimensions and the current CUDA stream; no torch types cross the
+boundary.  There is deliberately NO fallback: if the library is missing, or a tensor is not a CUDA fp64
+tensor, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgpb200.so")
+
+c_int, c_long, c_double, c_void_p, c_size_t = (
+    ctypes.c_int,
+    ctypes.c_long,
+    ctypes.c_double,
+    ctypes.c_void_p,
+    ctypes.c_size_t,
+)
+
+# name -> (restype, argtypes); mirrors include/gpb200.h one to one.
+SIGNATURES = {
+    "gpb_version": (c_int, []),
+    "gpb_last_error": (ctypes.c_char_p, []),
+    "gpb_block_size": (c_int, []),
+    "gpb_kern_fwd": (c_int, [c_int, c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_int,
+                             c_void_p, c_void_p, c_int, c_void_p, c_long, c_void_p]),
+    "gpb_kern_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gpb_kern_bwd": (c_int, [c_int, c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_int,
+                             c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
+    "gpb_linear_kdiag": (c_int, [c_void_p, c_int, c_long, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpb_potrf_lower": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_void_p]),
+    "gpb_tri_diag_inverse": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p]),
+    "gpb_potri_workspace_bytes": (c_size_t, [c_int]),
+    "gpb_potri_lower": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpb_potri_assemble": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_long, c_void_p]),
+    "gpb_tri_zero_upper": (c_int, [c_void_p, c_int, c_long, c_void_p]),
+    "gpb_add_diag": (c_int, [c_void_p, c_int, c_long, c_void_p, c_double, c_void_p]),
+    "gpb_trsv_workspace_bytes": (c_size_t, [c_int]),
+    "gpb_trsv_lower": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_int, c_long, c_int, c_void_p,
+                               c_size_t, c_void_p]),
+    "gpb_trsm_right_lt": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_int, c_long, c_void_p]),
+    "gpb_logdet_sumsq": (c_int, [c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_void_p, c_void_p]),
+    "gpb_gemm": (c_int, [c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double,
+                         c_void_p, c_long, c_int, c_void_p]),
+    "gpb_gpr_grad_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gpb_gpr_grad": (c_int, [c_int, c_void_p, c_int, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_long,
+                             c_void_p, c_void_p, c_int, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
+}
+
+_ERRORS = {-1: "bad argument", -2: "alignment (16-byte base, even leading dimension required)",
+           -3: "CUDA runtime error", -4: "CUDA driver / tensor-map error", -5: "unsupported configuration"}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    """libgpb200.so is missing or rejected a call.  (A RuntimeError subclass, but raised for argument and
+    environment problems only -- numerical failure of a factorisation is reported through ``info``.)"""
+
+
+def load():
+    """Load libgpb200.so and type every entry point.  Raises if the library is absent (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            "libgpb200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C gptorch_b200/csrc`.  gptorch_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def is_loaded():
+    return _lib is not None
+
+
+def _check(rc, what):
+    if rc != 0:
+        lib = load()
+        detail = lib.gpb_last_error().decode("utf-8", "replace")
+        raise NativeLibraryError("%s failed: %s (rc=%d) %s" % (what, _ERRORS.get(rc, "unknown"), rc, detail))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a CUDA fp64 tensor (or NULL for None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeLibraryError("gptorch_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path"
+                                 % t.device.type)
+    if t.dtype != torch.float64 and t.dtype != torch.int32:
+        raise NativeLibraryError("expected float64, got %s" % t.dtype)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    _check(rc, name)
+
+
+def query(name, *args):
+    """Call a size-returning entry point."""
+    lib = load()
+    return getattr(lib, name)(*args)

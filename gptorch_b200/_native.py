@@ -1,0 +1,232 @@
+"""Functional (non-autograd) wrappers over the C ABI: allocate outputs/workspaces with torch, pass raw pointers.
+
+torch is used here for device memory and the current stream only; every computation happens in
+libgpb200.so.  Shapes follow the reference: row-major fp64 2-D tensors (gptorch/util.py:11-12).
+"""
+import torch
+
+from . import _lib
+from ._lib import ptr, stream_ptr, call, query
+
+NB = 128
+
+KIND = {"Rbf": 0, "SquaredExponential": 0, "Exp": 1, "Matern12": 1, "Matern32": 2, "Matern52": 3, "Linear": 4}
+KERN_LINEAR = 4
+
+
+def _c(t):
+    """Contiguous fp64 CUDA view of t (copies only when needed)."""
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    return t.contiguous()
+
+
+def _npad(n):
+    return (n + NB - 1) // NB * NB
+
+
+def _aligned_empty(rows, cols, device):
+    """rows x cols fp64 buffer whose leading dimension is even (TMA needs 16-byte row strides)."""
+    ld = cols + (cols & 1)
+    buf = torch.empty((rows, ld), dtype=torch.float64, device=device)
+    return buf, ld
+
+
+def _ws(nbytes, device):
+    return torch.empty((max(int(nbytes), 8) + 7) // 8, dtype=torch.float64, device=device)
+
+
+# ---------------------------------------------------------------------------------------------- covariance
+def kern_fwd(kind, X, X2, ell, sigma2, noise=None, lower=False, out=None, ldk=None):
+    """K(X, X2) [+ noise I].  ell: (1,) or (D,) tensor; sigma2: (1,) tensor (None for Linear)."""
+    X = _c(X)
+    n1, D = X.shape
+    if X2 is not None:
+        X2 = _c(X2)
+        n2 = X2.shape[0]
+        if X2.shape[1] != D:
+            raise ValueError("X and X2 have different input dimensions")
+    else:
+        n2 = n1
+    ell = _c(ell).reshape(-1)
+    if kind == KERN_LINEAR and ell.numel() != D:
+        raise ValueError("Linear kernel needs one variance per input dimension")
+    if out is None:
+        out, ldk = _aligned_empty(n1, n2, X.device)
+    if n1 == 0 or n2 == 0:
+        return out[:, :n2]
+    call("gpb_kern_fwd", kind, ptr(X), n1, X.stride(0), ptr(X2), n2, X2.stride(0) if X2 is not None else 0, D,
+         ptr(ell), ell.numel(), ptr(_c(sigma2).reshape(-1)) if sigma2 is not None else None,
+         ptr(_c(noise).reshape(-1)) if noise is not None else None, 1 if lower else 0, ptr(out), ldk, stream_ptr())
+    return out[:, :n2]
+
+
+def kern_bwd(kind, X, X2, ell, sigma2, G, need_gx2, g_transposed=False):
+    """Reduce G = dLoss/dK against dK/d(ell, sigma2[, X2]).  Returns (g_ell, g_sigma2, gX2 or None)."""
+    X = _c(X)
+    n1, D = X.shape
+    X2c = _c(X2) if X2 is not None else X
+    n2 = X2c.shape[0]
+    ell = _c(ell).reshape(-1)
+    G = _c(G)
+    g_ell = torch.empty(ell.numel(), dtype=torch.float64, device=X.device)
+    g_sig = torch.empty(1, dtype=torch.float64, device=X.device)
+    gX2 = torch.empty((n2, D), dtype=torch.float64, device=X.device) if need_gx2 else None
+    ws_bytes = query("gpb_kern_bwd_workspace_bytes", n1, n2, D)
+    ws = _ws(ws_bytes, X.device)
+    call("gpb_kern_bwd", kind, ptr(X), n1, X.stride(0), ptr(X2c), n2, X2c.stride(0), D, ptr(ell), ell.numel(),
+         ptr(_c(sigma2).reshape(-1)) if sigma2 is not None else None, ptr(G), G.stride(0), 1 if g_transposed else 0,
+         ptr(g_ell), ptr(g_sig), ptr(gX2), ptr(ws), ws.numel() * 8, stream_ptr())
+    return g_ell, g_sig, gX2
+
+
+def linear_kdiag(X, v):
+    X = _c(X)
+    out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
+    if X.shape[0]:
+        call("gpb_linear_kdiag", ptr(X), X.shape[0], X.stride(0), X.shape[1], ptr(_c(v).reshape(-1)), ptr(out),
+             stream_ptr())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- Cholesky
+def potrf_(A, lda):
+    """In-place lower Cholesky of the n x n matrix in the (n, lda) buffer A.  Returns (dinv, info) where info
+    is a device int32 tensor (0 = success, k = first non-positive pivot, LAPACK convention)."""
+    n = A.shape[0]
+    dinv = torch.empty((_npad(n), NB), dtype=torch.float64, device=A.device)
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    call("gpb_potrf_lower", ptr(A), n, lda, ptr(dinv), ptr(info), stream_ptr())
+    return dinv, info
+
+
+def tri_diag_inverse(L):
+    n = L.shape[0]
+    dinv = torch.empty((_npad(n), NB), dtype=torch.float64, device=L.device)
+    call("gpb_tri_diag_inverse", ptr(L), n, L.stride(0), ptr(dinv), stream_ptr())
+    return dinv
+
+
+def potri_(A, lda, dinv):
+    """In place: strictly-lower blocks of A <- (L L^T)^-1; returns the diagonal 128-blocks (npad x 128)."""
+    n = A.shape[0]
+    kd = torch.empty((_npad(n), NB), dtype=torch.float64, device=A.device)
+    ws_bytes = query("gpb_potri_workspace_bytes", n)
+    ws = _ws(ws_bytes, A.device)
+    call("gpb_potri_lower", ptr(A), n, lda, ptr(dinv), ptr(kd), ptr(ws), ws.numel() * 8, stream_ptr())
+    return kd
+
+
+def potri_assemble(A, lda, kd):
+    n = A.shape[0]
+    out = torch.empty((n, n), dtype=torch.float64, device=A.device)
+    call("gpb_potri_assemble", ptr(A), n, lda, ptr(kd), ptr(out), n, stream_ptr())
+    return out
+
+
+def tri_zero_upper_(A, lda):
+    call("gpb_tri_zero_upper", ptr(A), A.shape[0], lda, stream_ptr())
+
+
+def add_diag_(A, lda, value):
+    """A += value * I; value is a python float or a 1-element device tensor."""
+    if isinstance(value, torch.Tensor):
+        call("gpb_add_diag", ptr(A), A.shape[0], lda, ptr(_c(value).reshape(-1)), 0.0, stream_ptr())
+    else:
+        call("gpb_add_diag", ptr(A), A.shape[0], lda, None, float(value), stream_ptr())
+
+
+def sym_buffer_from(x):
+    """Copy a square matrix into a fresh TMA-aligned (n, ld) buffer; returns (buffer, ld)."""
+    n = x.shape[0]
+    buf, ld = _aligned_empty(n, n, x.device)
+    buf[:, :n].copy_(x)
+    return buf, ld
+
+
+# ---------------------------------------------------------------------------------------------- solves
+def trsv_(L, dinv, B, trans):
+    """B <- L^-1 B (trans=False) or L^-T B (trans=True), in place; B is (n, k) contiguous."""
+    n, k = B.shape
+    ws_bytes = query("gpb_trsv_workspace_bytes", n)
+    ws = _ws(ws_bytes, B.device)
+    call("gpb_trsv_lower", ptr(L), n, L.stride(0), ptr(dinv), ptr(B), k, B.stride(0), 1 if trans else 0, ptr(ws),
+         ws.numel() * 8, stream_ptr())
+    return B
+
+
+def trsm_right_lt_(L, dinv, X, ldx):
+    """X <- X L^-T for the (m, n) panel stored in the (m, ldx) buffer X."""
+    m = X.shape[0]
+    n = L.shape[0]
+    call("gpb_trsm_right_lt", ptr(L), n, L.stride(0), ptr(dinv), ptr(X), m, ldx, stream_ptr())
+    return X
+
+
+def logdet_sumsq(L, V=None):
+    """Returns a 2-element device tensor: [sum log diag L, sum V^2]."""
+    out = torch.empty(2, dtype=torch.float64, device=L.device)
+    n = L.shape[0]
+    if V is not None:
+        call("gpb_logdet_sumsq", ptr(L), n, L.stride(0), ptr(V), V.shape[1], V.stride(0), ptr(out), stream_ptr())
+    else:
+        call("gpb_logdet_sumsq", ptr(L), n, L.stride(0), None, 0, 0, ptr(out), stream_ptr())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+GEMM_NT, GEMM_TN, GEMM_NN = 0, 1, 2
+
+
+def _gemm_operand(t):
+    """Return a contiguous fp64 tensor with even row stride and 16-byte aligned base (copying if needed)."""
+    t = _c(t)
+    if (t.stride(0) & 1) or (t.data_ptr() & 15):
+        buf, ld = _aligned_empty(t.shape[0], t.shape[1], t.device)
+        buf[:, : t.shape[1]].copy_(t)
+        return buf[:, : t.shape[1]]
+    return t
+
+
+def gemm(mode, A, B, alpha=1.0, beta=0.0, C=None, lower_only=False):
+    """C = alpha op(A) op(B) + beta C on the DMMA engine.  mode: GEMM_NT (A B^T), GEMM_TN (A^T B), GEMM_NN."""
+    A = _gemm_operand(A)
+    B = _gemm_operand(B)
+    if mode == GEMM_NT:
+        m, k = A.shape
+        n = B.shape[0]
+        kb = B.shape[1]
+    elif mode == GEMM_TN:
+        k, m = A.shape
+        kb, n = B.shape
+    else:
+        m, k = A.shape
+        kb, n = B.shape
+    if k != kb:
+        raise ValueError("gemm: inner dimensions differ (%d vs %d)" % (k, kb))
+    if C is None:
+        buf, ldc = _aligned_empty(m, n, A.device)
+        C = buf[:, :n]
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an existing C")
+    call("gpb_gemm", mode, m, n, k, float(alpha), ptr(A), A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C),
+         C.stride(0), 1 if lower_only else 0, stream_ptr())
+    return C
+
+
+# ---------------------------------------------------------------------------------------------- fused GPR gradient
+def gpr_grad(kind, X, ell, sigma2, Kinv, ldk, kd, a):
+    """Returns (g_ell, g_sigma2, g_noise): d loss / d (ell, sigma2, sigma_n^2) for the GPR loss."""
+    X = _c(X)
+    n, D = X.shape
+    ell = _c(ell).reshape(-1)
+    a = _c(a)
+    g_ell = torch.empty(ell.numel(), dtype=torch.float64, device=X.device)
+    g_sig = torch.zeros(1, dtype=torch.float64, device=X.device)
+    g_noise = torch.empty(1, dtype=torch.float64, device=X.device)
+    ws_bytes = query("gpb_gpr_grad_workspace_bytes", n, D)
+    ws = _ws(ws_bytes, X.device)
+    call("gpb_gpr_grad", kind, ptr(X), n, X.stride(0), D, ptr(ell), ell.numel(),
+         ptr(_c(sigma2).reshape(-1)) if sigma2 is not None else None, ptr(Kinv), ldk, ptr(kd), ptr(a), a.shape[1],
+         a.stride(0), ptr(g_ell), ptr(g_sig), ptr(g_noise), ptr(ws), ws.numel() * 8, stream_ptr())
+    return g_ell, g_sig, g_noise

@@ -1,0 +1,136 @@
+// gpb_api.cu -- the extern "C" boundary of libgpb200.so (declared in include/gpb200.h).
+#include "gpb_gemm.cuh"
+#include "../../include/gpb200.h"
+
+namespace gpb {
+const char* last_error();
+void set_last_error_msg(const char* msg);
+int potrf_lower(double* A, int n, long lda, double* dinv, int* info, cudaStream_t stream);
+int trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* X, int m, long ldx, cudaStream_t stream);
+int tri_diag_inverse(const double* L, int n, long ldl, double* dinv, cudaStream_t stream);
+size_t potri_workspace_bytes(int n);
+int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
+int potri_assemble(const double* A, int n, long lda, const double* kd, double* out, long ldo, cudaStream_t stream);
+size_t trsv_workspace_bytes(int n);
+int trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, int k, long ldb, int trans,
+               void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out, cudaStream_t stream);
+int tri_zero_upper(double* A, int n, long lda, cudaStream_t stream);
+int add_diag(double* A, int n, long lda, const double* value, double host_value, cudaStream_t stream);
+int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+             const double* ell, int ell_len, const double* sigma2, const double* noise, int fill, double* K,
+             long ldk, cudaStream_t stream);
+size_t kern_bwd_workspace_bytes(int n1, int n2, int D);
+int kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+             const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
+             double* g_ell, double* g_sigma2, double* gX2, void* workspace, size_t workspace_bytes,
+             cudaStream_t stream);
+int linear_kdiag(const double* X, int n, long ldx, int D, const double* v, double* out, cudaStream_t stream);
+size_t gpr_grad_workspace_bytes(int n, int D);
+int gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* ell, int ell_len,
+             const double* sigma2, const double* Kinv, long ldk, const double* kdiag_blocks, const double* a,
+             int dy, long lda_a, double* g_ell, double* g_sigma2, double* g_noise, void* workspace,
+             size_t workspace_bytes, cudaStream_t stream);
+}  // namespace gpb
+
+using namespace gpb;
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int gpb_version(void) { return 100; }
+const char* gpb_last_error(void) { return last_error(); }
+int gpb_block_size(void) { return NB; }
+
+int gpb_kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                 const double* ell, int ell_len, const double* sigma2, const double* noise, int fill, double* K,
+                 long ldk, void* stream) {
+  return kern_fwd(kind, X, n1, ldx, X2, n2, ldx2, D, ell, ell_len, sigma2, noise, fill, K, ldk, S(stream));
+}
+size_t gpb_kern_bwd_workspace_bytes(int n1, int n2, int D) { return kern_bwd_workspace_bytes(n1, n2, D); }
+int gpb_kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                 const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
+                 double* g_ell, double* g_sigma2, double* gX2, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  return kern_bwd(kind, X, n1, ldx, X2, n2, ldx2, D, ell, ell_len, sigma2, G, ldg, g_transposed, g_ell, g_sigma2,
+                  gX2, workspace, workspace_bytes, S(stream));
+}
+int gpb_linear_kdiag(const double* X, int n, long ldx, int D, const double* v, double* out, void* stream) {
+  return linear_kdiag(X, n, ldx, D, v, out, S(stream));
+}
+
+int gpb_potrf_lower(double* A, int n, long lda, double* dinv, int* info, void* stream) {
+  return potrf_lower(A, n, lda, dinv, info, S(stream));
+}
+int gpb_tri_diag_inverse(const double* L, int n, long ldl, double* dinv, void* stream) {
+  return tri_diag_inverse(L, n, ldl, dinv, S(stream));
+}
+size_t gpb_potri_workspace_bytes(int n) { return potri_workspace_bytes(n); }
+int gpb_potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return potri_lower(A, n, lda, dinv, kdiag_blocks, workspace, workspace_bytes, S(stream));
+}
+int gpb_potri_assemble(const double* A, int n, long lda, const double* kdiag_blocks, double* out, long ldo,
+                       void* stream) {
+  return potri_assemble(A, n, lda, kdiag_blocks, out, ldo, S(stream));
+}
+int gpb_tri_zero_upper(double* A, int n, long lda, void* stream) { return tri_zero_upper(A, n, lda, S(stream)); }
+int gpb_add_diag(double* A, int n, long lda, const double* value, double host_value, void* stream) {
+  return add_diag(A, n, lda, value, host_value, S(stream));
+}
+
+size_t gpb_trsv_workspace_bytes(int n) { return trsv_workspace_bytes(n); }
+int gpb_trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, int k, long ldb, int trans,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  return trsv_lower(L, n, ldl, dinv, B, k, ldb, trans, workspace, workspace_bytes, S(stream));
+}
+int gpb_trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* X, int m, long ldx,
+                      void* stream) {
+  return trsm_right_lt(L, n, ldl, dinv, X, m, ldx, S(stream));
+}
+int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out, void* stream) {
+  return logdet_sumsq(L, n, ldl, V, k, ldv, out, S(stream));
+}
+
+int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,
+             double beta, double* C, long ldc, int lower_only, void* stream) {
+  if (mode < 0 || mode > 2 || m < 0 || n < 0 || k < 0) return GPB_ERR_BADARG;
+  if (m == 0 || n == 0) return GPB_OK;
+  if (!A || !B || !C) return GPB_ERR_BADARG;
+  const GemmMode gm = static_cast<GemmMode>(mode);
+  CUtensorMap mapA, mapB;
+  // A is stored (m x k) for NT/NN and (k x m) for TN; B is (n x k) for NT and (k x n) for TN/NN.
+  const long a_rows = gm == GEMM_TN ? k : m, a_cols = gm == GEMM_TN ? m : k;
+  const long b_rows = gm == GEMM_NT ? n : k, b_cols = gm == GEMM_NT ? k : n;
+  if (k > 0) {
+    int rc = make_tmap_f64(&mapA, A, a_rows, a_cols, lda, gemm_box_rows_a(gm));
+    if (rc) return rc;
+    rc = make_tmap_f64(&mapB, B, b_rows, b_cols, ldb, gemm_box_rows_b(gm));
+    if (rc) return rc;
+  } else {
+    // k == 0: C = beta * C; the maps are never dereferenced but must be valid objects
+    int rc = make_tmap_f64(&mapA, C, m, n, ldc, 16);
+    if (rc) return rc;
+    mapB = mapA;
+  }
+  GemmArgs g;
+  g.M = m; g.N = n; g.K = k;
+  g.alpha = alpha; g.beta = beta;
+  g.C = C; g.ldc = ldc;
+  g.flags = lower_only ? GF_LOWER_TILES : 0u;
+  return gemm_launch(gm, mapA, mapB, g, S(stream));
+}
+
+size_t gpb_gpr_grad_workspace_bytes(int n, int D) { return gpr_grad_workspace_bytes(n, D); }
+int gpb_gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* ell, int ell_len,
+                 const double* sigma2, const double* Kinv, long ldk, const double* kdiag_blocks, const double* a,
+                 int dy, long lda_a, double* g_ell, double* g_sigma2, double* g_noise, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  return gpr_grad(kind, X, n, ldx, D, ell, ell_len, sigma2, Kinv, ldk, kdiag_blocks, a, dy, lda_a, g_ell, g_sigma2,
+                  g_noise, workspace, workspace_bytes, S(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

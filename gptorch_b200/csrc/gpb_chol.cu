@@ -1,0 +1,474 @@
+// gpb_chol.cu -- blocked FP64 Cholesky, triangular inverse and (L L^T)^-1 on the DMMA GEMM engine.
+//
+// Replaces torch.cholesky / torch.cholesky_inverse behind gptorch/functions.py:46-54 and the O(N^3) part of
+// autograd's CholeskyBackward0 in the GPR loss gradient.
+//
+// All matrices are row-major, LOWER storage.  Everything O(n^3) is expressed as NT / TN GEMMs on 128-aligned
+// sub-blocks addressed through ONE whole-buffer TMA tensor map, so a recursion step is just new coordinates:
+//
+//   potrf(A):   A11 = L11 L11^T (recurse) ; A21 <- A21 L11^-T (right TRSM, recursive, base case = NT GEMM with
+//               the explicit inverse of a 128x128 diagonal block) ; A22 -= A21 A21^T (SYRK, lower tiles) ;
+//               recurse on A22.  The 128x128 diagonal blocks are factored AND inverted in shared memory by
+//               one CTA (diag_block_kernel); the inverses are kept in `dinv` for every later solve.
+//   potri(L):   T = L^-T is built in the UPPER triangle of the same buffer, level by level (all sub-problems
+//               of one size are batched in one launch):  P^T = T22^T L21 (TN, triangular k-range),
+//               T12 = -T11 P  (NT, triangular k-range).  Then Kinv = T T^T (NT, k >= row-tile) is written
+//               to the strictly-lower blocks; diagonal blocks go to a side buffer because the diagonal
+//               blocks of T are still being read by other CTAs.
+#include "gpb_gemm.cuh"
+#include <algorithm>
+
+namespace gpb {
+
+void set_last_error_msg(const char* msg);
+
+// ================================================================================================
+// 128 x 128 diagonal block: Cholesky + inverse in shared memory (one CTA)
+// ================================================================================================
+constexpr int DG_THREADS = 512;
+constexpr int DG_LD = 129;
+constexpr int DG_SMEM_BYTES = (NB * DG_LD + 2 * NB) * 8 + 16;
+
+// A: pointer to the block's (0,0) element; nb <= 128 valid rows/cols (rest is treated as identity).
+// dinv_blk: 128 x 128 (ld 128) output, inverse of the (padded) lower factor, zeros above the diagonal.
+__global__ void __launch_bounds__(DG_THREADS, 1)
+diag_block_kernel(double* __restrict__ A, long lda, int nb, double* __restrict__ dinv_blk, int* info, int j0,
+                  int do_factor) {
+  extern __shared__ double dg_smem[];
+  double* S = dg_smem;                 // [128][129]; lower: L ; S[c][i+1] (i>c): inverse entry (i,c)
+  double* rsq = S + NB * DG_LD;        // 1/sqrt(pivot_k)
+  double* invd = rsq + NB;             // 1/L_kk
+  const int t = threadIdx.x;
+
+  for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    double v = 0.0;
+    if (c <= r) {
+      if (r < nb) v = A[static_cast<long>(r) * lda + c];
+      else v = (r == c) ? 1.0 : 0.0;
+    }
+    S[r * DG_LD + c] = v;
+  }
+
+  const int row = t >> 2, q = t & 3;
+  if (do_factor) {
+    // Right-looking, one barrier per column.  Column k is never rescaled in place (other rows read it
+    // un-scaled during step k); the scale 1/sqrt(pivot) is applied on the fly and once more at the end.
+    for (int k = 0; k < NB; ++k) {
+      __syncthreads();
+      const double d = S[k * DG_LD + k];
+      if (!(d > 0.0)) {
+        // LAPACK potrf: first non-positive (or NaN) pivot -> info = its 1-based index; keep going with NaNs.
+        if (t == 0 && k < nb && atomicCAS(info, 0, j0 + k + 1) == 0) { /* recorded */ }
+      }
+      const double rs = 1.0 / sqrt(d);
+      if (t == 0) rsq[k] = rs;
+      if (row > k) {
+        const double lik = S[row * DG_LD + k] * rs;
+        for (int j = k + 1 + q; j <= row; j += 4) {
+          const double ljk = S[j * DG_LD + k] * rs;
+          S[row * DG_LD + j] -= lik * ljk;
+        }
+      }
+    }
+    __syncthreads();
+    // final scaling: L[i][k] = S[i][k] * rsq[k] (i > k), L[k][k] = sqrt(pivot) = pivot * rsq[k]
+    for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
+      const int r = idx >> 7, c = idx & 127;
+      if (c <= r) S[r * DG_LD + c] *= rsq[c];
+    }
+  }
+  __syncthreads();
+  if (t < NB) invd[t] = 1.0 / S[t * DG_LD + t];
+  __syncthreads();
+
+  // ---- inverse: 4 lanes per column c, forward substitution  x_i = -(sum_{k=c}^{i-1} L_ik x_k) / L_ii ------
+  {
+    const int c = row;
+    const int cmin = (t >> 5) * 8;  // smallest column handled by this warp (uniform loop bounds)
+    const double xc = invd[c];
+    for (int i = cmin + 1; i < NB; ++i) {
+      double part = 0.0;
+      if (i > c) {
+        for (int k = c + q; k < i; k += 4) {
+          const double xk = (k == c) ? xc : S[c * DG_LD + k + 1];
+          part += S[i * DG_LD + k] * xk;
+        }
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      if (i > c && q == 0) S[c * DG_LD + i + 1] = -part * invd[i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  if (do_factor) {
+    for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
+      const int r = idx >> 7, c = idx & 127;
+      if (r < nb && c <= r) A[static_cast<long>(r) * lda + c] = S[r * DG_LD + c];
+    }
+  }
+  for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    double v = 0.0;
+    if (c < r) v = S[c * DG_LD + r + 1];
+    else if (c == r) v = invd[r];
+    dinv_blk[r * NB + c] = v;
+  }
+}
+
+static int launch_diag_block(double* A, long lda, int nb, double* dinv_blk, int* info, int j0, int do_factor,
+                             cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPB_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
+    attr_set = true;
+  }
+  diag_block_kernel<<<1, DG_THREADS, DG_SMEM_BYTES, stream>>>(A, lda, nb, dinv_blk, info, j0, do_factor);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+// Batched variant for gpb_tri_diag_inverse (no factorisation): one CTA per diagonal block.
+__global__ void __launch_bounds__(DG_THREADS, 1)
+diag_inverse_batched_kernel(const double* __restrict__ L, long ldl, int n, double* __restrict__ dinv) {
+  extern __shared__ double dg_smem[];
+  double* S = dg_smem;
+  double* invd = S + NB * DG_LD + NB;
+  const int t = threadIdx.x;
+  const int j0 = blockIdx.x * NB;
+  const int nb = min(NB, n - j0);
+  const double* A = L + static_cast<long>(j0) * ldl + j0;
+  for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    double v = 0.0;
+    if (c <= r) {
+      if (r < nb) v = A[static_cast<long>(r) * ldl + c];
+      else v = (r == c) ? 1.0 : 0.0;
+    }
+    S[r * DG_LD + c] = v;
+  }
+  __syncthreads();
+  if (t < NB) invd[t] = 1.0 / S[t * DG_LD + t];
+  __syncthreads();
+  const int c = t >> 2, q = t & 3;
+  const int cmin = (t >> 5) * 8;
+  const double xc = invd[c];
+  for (int i = cmin + 1; i < NB; ++i) {
+    double part = 0.0;
+    if (i > c) {
+      for (int k = c + q; k < i; k += 4) {
+        const double xk = (k == c) ? xc : S[c * DG_LD + k + 1];
+        part += S[i * DG_LD + k] * xk;
+      }
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (i > c && q == 0) S[c * DG_LD + i + 1] = -part * invd[i];
+    __syncwarp();
+  }
+  __syncthreads();
+  double* out = dinv + static_cast<long>(j0) * NB;
+  for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
+    const int r = idx >> 7, cc = idx & 127;
+    double v = 0.0;
+    if (cc < r) v = S[cc * DG_LD + r + 1];
+    else if (cc == r) v = invd[r];
+    out[r * NB + cc] = v;
+  }
+}
+
+// ================================================================================================
+// potrf driver
+// ================================================================================================
+struct CholCtx {
+  double* A;
+  long lda;
+  int n;
+  double* dinv;
+  int* info;
+  CUtensorMap mapA128;   // whole buffer, box rows 128
+  CUtensorMap mapD128;   // dinv [npad x 128], box rows 128
+  cudaStream_t stream;
+};
+
+static inline int split_point(int n) {
+  // first part: floor(half of the 128-blocks) * 128  (>= 128 because n > 128)
+  const int nblk = (n + NB - 1) / NB;
+  return (nblk / 2) * NB;
+}
+
+// X[r0:r0+m, c0:c0+n] <- X * L[c0:c0+n, c0:c0+n]^-T
+static int trsm_right_rec(CholCtx& c, int r0, int m, int c0, int n) {
+  if (m <= 0 || n <= 0) return GPB_OK;
+  if (n <= NB) {
+    GemmArgs g;
+    g.M = m; g.N = n; g.K = NB;
+    g.alpha = 1.0; g.beta = 0.0;
+    g.C = c.A + static_cast<long>(r0) * c.lda + c0;
+    g.ldc = c.lda;
+    g.ax = c0; g.ay = r0;
+    g.bx = 0; g.by = c0;
+    return gemm_launch(GEMM_NT, c.mapA128, c.mapD128, g, c.stream);
+  }
+  const int n1 = split_point(n), n2 = n - n1;
+  int rc = trsm_right_rec(c, r0, m, c0, n1);
+  if (rc) return rc;
+  GemmArgs g;
+  g.M = m; g.N = n2; g.K = n1;
+  g.alpha = -1.0; g.beta = 1.0;
+  g.C = c.A + static_cast<long>(r0) * c.lda + c0 + n1;
+  g.ldc = c.lda;
+  g.ax = c0; g.ay = r0;
+  g.bx = c0; g.by = c0 + n1;
+  rc = gemm_launch(GEMM_NT, c.mapA128, c.mapA128, g, c.stream);
+  if (rc) return rc;
+  return trsm_right_rec(c, r0, m, c0 + n1, n2);
+}
+
+static int potrf_rec(CholCtx& c, int j0, int n) {
+  if (n <= 0) return GPB_OK;
+  if (n <= NB) {
+    return launch_diag_block(c.A + static_cast<long>(j0) * c.lda + j0, c.lda, n, c.dinv + static_cast<long>(j0) * NB,
+                             c.info, j0, 1, c.stream);
+  }
+  const int n1 = split_point(n), n2 = n - n1;
+  int rc = potrf_rec(c, j0, n1);
+  if (rc) return rc;
+  rc = trsm_right_rec(c, j0 + n1, n2, j0, n1);
+  if (rc) return rc;
+  GemmArgs g;
+  g.M = n2; g.N = n2; g.K = n1;
+  g.alpha = -1.0; g.beta = 1.0;
+  g.C = c.A + static_cast<long>(j0 + n1) * c.lda + (j0 + n1);
+  g.ldc = c.lda;
+  g.ax = j0; g.ay = j0 + n1;
+  g.bx = j0; g.by = j0 + n1;
+  g.flags = GF_LOWER_TILES;
+  rc = gemm_launch(GEMM_NT, c.mapA128, c.mapA128, g, c.stream);
+  if (rc) return rc;
+  return potrf_rec(c, j0 + n1, n2);
+}
+
+static inline long npad128(long n) { return (n + NB - 1) / NB * NB; }
+
+int potrf_lower(double* A, int n, long lda, double* dinv, int* info, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  if (!A || !dinv || !info || lda < n) return GPB_ERR_BADARG;
+  CholCtx c;
+  c.A = A; c.lda = lda; c.n = n; c.dinv = dinv; c.info = info; c.stream = stream;
+  int rc = make_tmap_f64(&c.mapA128, A, n, n, lda, 128);
+  if (rc) return rc;
+  rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 128);
+  if (rc) return rc;
+  return potrf_rec(c, 0, n);
+}
+
+int trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* X, int m, long ldx,
+                  cudaStream_t stream);
+
+// ================================================================================================
+// right-side solve on a separate panel X (m x n):  X <- X L^-T
+// ================================================================================================
+struct TrsmCtx {
+  double* X; long ldx; int m;
+  CUtensorMap mapX128, mapL128, mapD128;
+  cudaStream_t stream;
+};
+
+static int trsm_panel_rec(TrsmCtx& c, int c0, int n) {
+  if (n <= 0) return GPB_OK;
+  if (n <= NB) {
+    GemmArgs g;
+    g.M = c.m; g.N = n; g.K = NB;
+    g.alpha = 1.0; g.beta = 0.0;
+    g.C = c.X + c0; g.ldc = c.ldx;
+    g.ax = c0; g.ay = 0;
+    g.bx = 0; g.by = c0;
+    return gemm_launch(GEMM_NT, c.mapX128, c.mapD128, g, c.stream);
+  }
+  const int n1 = split_point(n), n2 = n - n1;
+  int rc = trsm_panel_rec(c, c0, n1);
+  if (rc) return rc;
+  GemmArgs g;
+  g.M = c.m; g.N = n2; g.K = n1;
+  g.alpha = -1.0; g.beta = 1.0;
+  g.C = c.X + c0 + n1; g.ldc = c.ldx;
+  g.ax = c0; g.ay = 0;
+  g.bx = c0; g.by = c0 + n1;
+  rc = gemm_launch(GEMM_NT, c.mapX128, c.mapL128, g, c.stream);
+  if (rc) return rc;
+  return trsm_panel_rec(c, c0 + n1, n2);
+}
+
+int trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* X, int m, long ldx,
+                  cudaStream_t stream) {
+  if (n <= 0 || m <= 0) return GPB_OK;
+  if (!L || !dinv || !X || ldl < n || ldx < n) return GPB_ERR_BADARG;
+  TrsmCtx c;
+  c.X = X; c.ldx = ldx; c.m = m; c.stream = stream;
+  int rc = make_tmap_f64(&c.mapX128, X, m, n, ldx, 128);
+  if (rc) return rc;
+  rc = make_tmap_f64(&c.mapL128, L, n, n, ldl, 128);
+  if (rc) return rc;
+  rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 128);
+  if (rc) return rc;
+  return trsm_panel_rec(c, 0, n);
+}
+
+int tri_diag_inverse(const double* L, int n, long ldl, double* dinv, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  if (!L || !dinv || ldl < n) return GPB_ERR_BADARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPB_CUDA_CHECK(cudaFuncSetAttribute(diag_inverse_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        DG_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int nblk = (n + NB - 1) / NB;
+  diag_inverse_batched_kernel<<<nblk, DG_THREADS, DG_SMEM_BYTES, stream>>>(L, ldl, n, dinv);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+// ================================================================================================
+// potri: T = L^-T in the upper triangle, then Kinv = T T^T
+// ================================================================================================
+// Base case: diagonal block j of the buffer <- transpose(dinv block j) (upper triangular, zeros below).
+__global__ void __launch_bounds__(256) tinv_base_kernel(double* __restrict__ A, long lda, int n,
+                                                        const double* __restrict__ dinv) {
+  __shared__ double tile[32][33];
+  const int j0 = blockIdx.z * NB;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // output tile: rows by.., cols bx.. inside the block
+  const double* D = dinv + static_cast<long>(j0) * NB;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  // read dinv[(bx + i)][by + tx] -> tile[i][tx]   (transposed source tile)
+  for (int i = ty; i < 32; i += 8) tile[i][tx] = D[(bx + i) * NB + by + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int r = by + i, c = bx + tx;  // output (r, c) = dinv[c][r], upper triangular
+    if (j0 + r < n && j0 + c < n) {
+      const double v = (c >= r) ? tile[tx][i] : 0.0;
+      A[static_cast<long>(j0 + r) * lda + j0 + c] = v;
+    }
+  }
+}
+
+size_t potri_workspace_bytes(int n) {
+  // P^T scratch: max over levels s of (#problems at the level) * s * s doubles.
+  size_t best = 0;
+  for (long s = NB; s < n; s *= 2) {
+    long nprob = (n + 2 * s - 1) / (2 * s);
+    best = std::max(best, static_cast<size_t>(nprob) * s * s);
+  }
+  return best * sizeof(double) + 256;
+}
+
+int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  if (!A || !dinv || !kdiag_blocks || lda < n) return GPB_ERR_BADARG;
+  if (workspace_bytes < potri_workspace_bytes(n) || (n > NB && !workspace)) return GPB_ERR_BADARG;
+  const int nblk = (n + NB - 1) / NB;
+  {
+    dim3 grid(NB / 32, NB / 32, nblk);
+    tinv_base_kernel<<<grid, 256, 0, stream>>>(A, lda, n, dinv);
+    GPB_CUDA_CHECK(cudaGetLastError());
+  }
+  CUtensorMap mapA128, mapA16;
+  int rc = make_tmap_f64(&mapA128, A, n, n, lda, 128);
+  if (rc) return rc;
+  rc = make_tmap_f64(&mapA16, A, n, n, lda, 16);
+  if (rc) return rc;
+  double* W = static_cast<double*>(workspace);
+
+  for (long s = NB; s < n; s *= 2) {
+    // problems p = 0.. : block [p*2s, p*2s + 2s): T11 = first s, T22 = next n2 = min(s, n - p*2s - s) (> 0)
+    const int nfull = static_cast<int>(n / (2 * s));              // problems with n2 == s
+    const long rem = n - static_cast<long>(nfull) * 2 * s;        // leftover rows after the full problems
+    const int n2_last = rem > s ? static_cast<int>(rem - s) : 0;  // ragged problem (n2 < s) if any
+    CUtensorMap mapW128;
+    const int nprob = nfull + (n2_last > 0 ? 1 : 0);
+    if (nprob == 0) continue;
+    rc = make_tmap_f64(&mapW128, W, static_cast<long>(nprob) * s, s, s, 128);
+    if (rc) return rc;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int batch = pass == 0 ? nfull : (n2_last > 0 ? 1 : 0);
+      if (batch == 0) continue;
+      const int p0 = pass == 0 ? 0 : nfull;
+      const int n2 = pass == 0 ? static_cast<int>(s) : n2_last;
+      const int off = static_cast<int>(p0 * 2 * s);
+      // (1) P^T[n2 x s] = T22^T L21        TN, A = T22 (k <= m: GF_KHI_M), B = L21
+      GemmArgs g1;
+      g1.M = n2; g1.N = static_cast<int>(s); g1.K = n2;
+      g1.alpha = 1.0; g1.beta = 0.0;
+      g1.C = W + static_cast<long>(p0) * s * s; g1.ldc = s; g1.c_batch = s * s;
+      g1.ax = off + static_cast<int>(s); g1.ay = off + static_cast<int>(s);
+      g1.bx = off; g1.by = off + static_cast<int>(s);
+      g1.dax = g1.day = g1.dbx = g1.dby = static_cast<int>(2 * s);
+      g1.flags = GF_KHI_M;
+      g1.batch = batch;
+      rc = gemm_launch(GEMM_TN, mapA16, mapA16, g1, stream);
+      if (rc) return rc;
+      // (2) T12[s x n2] = -T11 (P^T)^T     NT, A = T11 (k >= m: GF_KLO_M), B = P^T (n2 x s)
+      GemmArgs g2;
+      g2.M = static_cast<int>(s); g2.N = n2; g2.K = static_cast<int>(s);
+      g2.alpha = -1.0; g2.beta = 0.0;
+      g2.C = A + static_cast<long>(off) * lda + off + s; g2.ldc = lda; g2.c_batch = 2 * s * (lda + 1);
+      g2.ax = off; g2.ay = off;
+      g2.dax = g2.day = static_cast<int>(2 * s);
+      g2.bx = 0; g2.by = static_cast<int>(p0 * s);
+      g2.dbx = 0; g2.dby = static_cast<int>(s);
+      g2.flags = GF_KLO_M;
+      g2.batch = batch;
+      rc = gemm_launch(GEMM_NT, mapA128, mapW128, g2, stream);
+      if (rc) return rc;
+    }
+  }
+  // Kinv = T T^T: strictly-lower blocks in place, diagonal blocks to kdiag_blocks.
+  GemmArgs g;
+  g.M = n; g.N = n; g.K = n;
+  g.alpha = 1.0; g.beta = 0.0;
+  g.C = A; g.ldc = lda;
+  g.Cdiag = kdiag_blocks; g.ldd = NB;
+  g.flags = GF_LOWER_TILES | GF_KLO_M | GF_DIAG_TO_WS;
+  return gemm_launch(GEMM_NT, mapA128, mapA128, g, stream);
+}
+
+// out (full symmetric) <- blocked potri result
+__global__ void __launch_bounds__(256) potri_assemble_kernel(const double* __restrict__ A, long lda, int n,
+                                                             const double* __restrict__ kd, double* __restrict__ out,
+                                                             long ldo) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;  // 32 x 32 tiles; only bj <= bi launched usefully
+  if (bj > bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = bi * 32, c0 = bj * 32;
+  const bool diag_blk = (r0 / NB) == (c0 / NB);
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    double v = 0.0;
+    if (r < n && c < n) v = diag_blk ? kd[static_cast<long>(r) * NB + (c - (c0 / NB) * NB)] : A[static_cast<long>(r) * lda + c];
+    tile[i][tx] = v;
+    if (r < n && c < n) out[static_cast<long>(r) * ldo + c] = v;
+  }
+  __syncthreads();
+  if (bi != bj) {
+    for (int i = ty; i < 32; i += 8) {
+      const int r = c0 + i, c = r0 + tx;  // mirrored position
+      if (r < n && c < n) out[static_cast<long>(r) * ldo + c] = tile[tx][i];
+    }
+  }
+}
+
+int potri_assemble(const double* A, int n, long lda, const double* kd, double* out, long ldo, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  const int nt = (n + 31) / 32;
+  dim3 grid(nt, nt);
+  potri_assemble_kernel<<<grid, 256, 0, stream>>>(A, lda, n, kd, out, ldo);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+}  // namespace gpb

@@ -1,0 +1,600 @@
+// gpb_kern.cu -- fused covariance construction and its gradient reductions.
+//
+// Forward (gpb_kern_fwd) replaces Kernel.K (gptorch/kernels.py:189-222, 258-262) together with
+// Stationary.squared_dist/dist (:149-172), util.squared_distance (gptorch/util.py:73-88) and the noise
+// diagonal of GPR._compute_kyy (gptorch/models/gpr.py:69-86): one pass, one N^2 write, no temporaries.
+// The X.X'^T term of the reference's expansion |a|^2 + |b|^2 - 2 a.b runs on FP64 DMMA; the clamp, sqrt,
+// kernel non-linearity, variance and noise are applied in the accumulator epilogue.
+//
+// Backward (gpb_kern_bwd / gpb_gpr_grad) replaces torch autograd through those composite ops: it reduces an
+// upstream gradient against dK/d(length scales, variance, X2) in one pass over G, recomputing K on the fly.
+// For the GPR loss the upstream gradient W = 1/2 (dy Kinv - a a^T) is itself formed on the fly from the
+// blocked inverse left by gpb_potri_lower, so neither W nor K is ever materialised.
+#include "gpb_common.cuh"
+#include <algorithm>
+
+namespace gpb {
+
+enum { KERN_RBF = 0, KERN_EXP = 1, KERN_MATERN32 = 2, KERN_MATERN52 = 3, KERN_LINEAR = 4 };
+
+#define SQRT3 1.7320508075688772
+#define SQRT5 2.23606797749979
+
+// value of the kernel divided by the variance, as a function of the (clamped) scaled squared distance.
+__device__ __forceinline__ double kern_base(int kind, double r2) {
+  if (kind == KERN_RBF) return exp(-0.5 * r2);
+  const double r = sqrt(fmax(r2, 1e-40));  // gptorch/kernels.py:172
+  if (kind == KERN_EXP) return exp(-r);
+  if (kind == KERN_MATERN32) {
+    const double r3 = SQRT3 * r;
+    return (1.0 + r3) * exp(-r3);
+  }
+  const double r5 = SQRT5 * r;  // MATERN52
+  return (1.0 + r5 + (5.0 / 3.0) * r * r) * exp(-r5);
+}
+
+// kbase = K / sigma2 ; fac1 = fac / sigma2 where dK/d log(ell_d) = fac * delta_d^2 / ell_d^2.
+__device__ __forceinline__ void kern_base_fac(int kind, double r2, double& kbase, double& fac1) {
+  if (kind == KERN_RBF) {
+    kbase = exp(-0.5 * r2);
+    fac1 = kbase;
+    return;
+  }
+  const bool clamped = r2 < 1e-40;  // sqrt-clamp: zero gradient below the clamp (gptorch/kernels.py:171-172)
+  const double r = sqrt(fmax(r2, 1e-40));
+  if (kind == KERN_EXP) {
+    const double e = exp(-r);
+    kbase = e;
+    fac1 = clamped ? 0.0 : e / r;
+  } else if (kind == KERN_MATERN32) {
+    const double r3 = SQRT3 * r, e = exp(-r3);
+    kbase = (1.0 + r3) * e;
+    fac1 = clamped ? 0.0 : 3.0 * e;
+  } else {
+    const double r5 = SQRT5 * r, e = exp(-r5);
+    kbase = (1.0 + r5 + (5.0 / 3.0) * r * r) * e;
+    fac1 = clamped ? 0.0 : (5.0 / 3.0) * (1.0 + r5) * e;
+  }
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+constexpr int KF_TILE = 128;
+constexpr int KF_DC = 16;    // feature chunk staged per pass
+constexpr int KF_LD = 20;    // padded row stride (doubles): 20 mod 16 == 4 -> conflict-free DMMA fragment loads
+constexpr int KF_THREADS = 256;
+
+struct KfwdParams {
+  int kind;
+  const double* X; int n1; long ldx;
+  const double* X2; int n2; long ldx2;
+  int D;
+  const double* ell; int ell_len;
+  const double* sigma2;
+  const double* noise;
+  int symmetric;   // X2 == NULL
+  int lower;       // only tiles with tn <= tm
+  double* K; long ldk;
+  int tiles_n;
+};
+
+__global__ void __launch_bounds__(KF_THREADS, 1) kern_fwd_kernel(const KfwdParams p) {
+  __shared__ double As[KF_TILE * KF_LD];
+  __shared__ double Bs[KF_TILE * KF_LD];
+  __shared__ double na[KF_TILE], nbv[KF_TILE];
+  __shared__ double scale[KF_DC];
+
+  int tm, tn;
+  {
+    const int t = blockIdx.x;
+    if (p.lower) {
+      int r = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while ((r + 1) * (r + 2) / 2 <= t) ++r;
+      while (r * (r + 1) / 2 > t) --r;
+      tm = r;
+      tn = t - r * (r + 1) / 2;
+    } else {
+      tm = t / p.tiles_n;
+      tn = t - tm * p.tiles_n;
+    }
+  }
+  const int m0 = tm * KF_TILE, n0 = tn * KF_TILE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 1, wn = warp >> 1;
+  const int r = lane >> 2, kk = lane & 3;
+  const bool linear = p.kind == KERN_LINEAR;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double my_na = 0.0, my_nb = 0.0;  // thread t < 128 accumulates the squared norm of row t of each operand
+
+  for (int d0 = 0; d0 < p.D; d0 += KF_DC) {
+    __syncthreads();
+    if (tid < KF_DC) {
+      const int d = d0 + tid;
+      double s = 1.0;
+      if (d < p.D) s = p.ell[p.ell_len == 1 ? 0 : d];
+      scale[tid] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < KF_TILE * KF_DC; idx += KF_THREADS) {
+      const int row = idx >> 4, k = idx & 15;
+      const int d = d0 + k;
+      double va = 0.0, vb = 0.0;
+      if (d < p.D) {
+        if (m0 + row < p.n1) {
+          const double x = p.X[static_cast<long>(m0 + row) * p.ldx + d];
+          va = linear ? x * scale[k] : x / scale[k];
+        }
+        if (n0 + row < p.n2) {
+          const double x = p.X2[static_cast<long>(n0 + row) * p.ldx2 + d];
+          vb = linear ? x : x / scale[k];
+        }
+      }
+      As[row * KF_LD + k] = va;
+      Bs[row * KF_LD + k] = vb;
+    }
+    __syncthreads();
+    if (tid < KF_TILE) {
+#pragma unroll
+      for (int k = 0; k < KF_DC; ++k) {
+        const double a = As[tid * KF_LD + k], b = Bs[tid * KF_LD + k];
+        my_na += a * a;
+        my_nb += b * b;
+      }
+    }
+#pragma unroll
+    for (int ks = 0; ks < KF_DC / 4; ++ks) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[(wm * 64 + 8 * i + r) * KF_LD + ks * 4 + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[(wn * 32 + 8 * j + r) * KF_LD + ks * 4 + kk];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  if (tid < KF_TILE) {
+    na[tid] = my_na;
+    nbv[tid] = my_nb;
+  }
+  __syncthreads();
+
+  const double sig2 = linear ? 1.0 : *p.sigma2;
+  const double noise = (p.symmetric && p.noise) ? *p.noise : 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int lr = wm * 64 + 8 * i + r;
+    const int row = m0 + lr;
+    if (row >= p.n1) continue;
+    const double nrow = na[lr];
+    double* krow = p.K + static_cast<long>(row) * p.ldk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int lc = wn * 32 + 8 * j + 2 * kk;
+      const int col = n0 + lc;
+      double v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double dot = acc[i][j][e];
+        if (linear) {
+          v[e] = dot;
+        } else {
+          double r2 = (nrow + nbv[lc + e]) - 2.0 * dot;  // gptorch/util.py:84
+          r2 = fmax(r2, 0.0);                             // value of r2 - clamp(r2, max=0) (gptorch/util.py:88)
+          v[e] = sig2 * kern_base(p.kind, r2);
+        }
+        if (p.symmetric && row == col + e) v[e] += noise;
+      }
+      if (col + 1 < p.n2 && ((p.ldk & 1) == 0)) {
+        *reinterpret_cast<double2*>(krow + col) = make_double2(v[0], v[1]);
+      } else {
+        if (col < p.n2) krow[col] = v[0];
+        if (col + 1 < p.n2) krow[col + 1] = v[1];
+      }
+    }
+  }
+}
+
+int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+             const double* ell, int ell_len, const double* sigma2, const double* noise, int fill, double* K,
+             long ldk, cudaStream_t stream) {
+  if (kind < 0 || kind > KERN_LINEAR) return GPB_ERR_BADARG;
+  if (!X || !K || !ell || D <= 0 || (ell_len != 1 && ell_len != D)) return GPB_ERR_BADARG;
+  if (kind != KERN_LINEAR && !sigma2) return GPB_ERR_BADARG;
+  if (kind == KERN_LINEAR && ell_len != D) return GPB_ERR_BADARG;
+  KfwdParams p;
+  p.kind = kind;
+  p.X = X; p.n1 = n1; p.ldx = ldx;
+  p.symmetric = (X2 == nullptr);
+  if (p.symmetric) { p.X2 = X; p.n2 = n1; p.ldx2 = ldx; }
+  else { p.X2 = X2; p.n2 = n2; p.ldx2 = ldx2; }
+  if (n1 <= 0 || p.n2 <= 0) return GPB_OK;
+  if (ldx < D || p.ldx2 < D || ldk < p.n2) return GPB_ERR_BADARG;
+  if (reinterpret_cast<uintptr_t>(K) & 15) return GPB_ERR_ALIGN;
+  p.D = D; p.ell = ell; p.ell_len = ell_len; p.sigma2 = sigma2; p.noise = noise;
+  p.lower = (fill == 1);
+  if (p.lower && !p.symmetric) return GPB_ERR_BADARG;
+  p.K = K; p.ldk = ldk;
+  const int tiles_m = (n1 + KF_TILE - 1) / KF_TILE;
+  p.tiles_n = (p.n2 + KF_TILE - 1) / KF_TILE;
+  const int ntiles = p.lower ? tiles_m * (tiles_m + 1) / 2 : tiles_m * p.tiles_n;
+  kern_fwd_kernel<<<ntiles, KF_THREADS, 0, stream>>>(p);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+// ================================================================================================
+// Linear.Kdiag
+// ================================================================================================
+__global__ void linear_kdiag_kernel(const double* __restrict__ X, int n, long ldx, int D, const double* __restrict__ v,
+                                    double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int d = 0; d < D; ++d) {
+    const double x = X[static_cast<long>(i) * ldx + d];
+    s += x * x * v[d];  // gptorch/kernels.py:265
+  }
+  out[i] = s;
+}
+
+int linear_kdiag(const double* X, int n, long ldx, int D, const double* v, double* out, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  if (!X || !v || !out || D <= 0) return GPB_ERR_BADARG;
+  linear_kdiag_kernel<<<(n + 255) / 256, 256, 0, stream>>>(X, n, ldx, D, v, out);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+// ================================================================================================
+// backward reductions
+// ================================================================================================
+constexpr int KB_COLS = 128;     // columns (second argument) per CTA, one per thread pair
+constexpr int KB_RT = 16;        // rows per thread per chunk
+constexpr int KB_ROWS = 2 * KB_RT;  // rows per chunk (two thread halves)
+constexpr int KB_THREADS = 256;
+constexpr int KB_DC = 16;        // accumulator chunk of feature dimensions
+constexpr int KB_DMAX = 160;     // shared-memory staging limit on D
+constexpr int KB_DY = 8;         // a-vector chunk
+
+struct KbwdParams {
+  int kind;
+  const double* X1; int n1; long ldx1;
+  const double* X2; int n2; long ldx2;
+  int D;
+  const double* ell; int ell_len;
+  const double* sigma2;
+  const double* G; long ldg; int g_trans;      // dense upstream gradient
+  const double* Kinv; long ldk; const double* kd; const double* a; int dy; long lda;  // GPR form
+  int strips, nrc;
+  double* part_h;    // [ncta][D + 2]: S_d ..., sum G*K/sigma2, tr W
+  double* part_g2;   // [strips][n2][D] or nullptr
+};
+
+template <bool GPR>
+__global__ void __launch_bounds__(KB_THREADS) kern_bwd_kernel(const KbwdParams p) {
+  extern __shared__ double kb_smem[];
+  const int D = p.D;
+  double* X2s = kb_smem;                       // [D][128]
+  double* X1s = X2s + static_cast<size_t>(D) * KB_COLS;    // [KB_ROWS][D]
+  double* ellv = X1s + static_cast<size_t>(KB_ROWS) * D;   // [D]
+  double* acol = ellv + D;                     // [128][KB_DY]
+  double* arow = acol + KB_COLS * KB_DY;       // [KB_ROWS][KB_DY]
+  double* red = arow + KB_ROWS * KB_DY;        // [32] + [2][128] combine scratch
+  double* comb = red + 32;
+
+  const int t = threadIdx.x, c = t & 127, half = t >> 7;
+  const int cb = blockIdx.x, strip = blockIdx.y;
+  const int c0 = cb * KB_COLS;
+  const int j = c0 + c;
+  const bool jvalid = j < p.n2;
+  const bool linear = p.kind == KERN_LINEAR;
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+
+  for (int d = t; d < D; d += KB_THREADS) ellv[d] = p.ell[p.ell_len == 1 ? 0 : d];
+  __syncthreads();
+  for (int idx = t; idx < KB_COLS * D; idx += KB_THREADS) {
+    const int cc = idx / D, d = idx - cc * D;
+    double v = 0.0;
+    if (c0 + cc < p.n2) {
+      v = p.X2[static_cast<long>(c0 + cc) * p.ldx2 + d];
+      if (!linear) v /= ellv[d];
+    }
+    X2s[d * KB_COLS + cc] = v;
+  }
+  const double sig2 = linear ? 1.0 : *p.sigma2;
+  // GPR: rows start at the column block's own 128-block (lower triangle only)
+  const int rc_start = GPR ? (c0 / KB_ROWS) : 0;
+
+  double sK = 0.0, gn = 0.0;
+  const int ndc = (D + KB_DC - 1) / KB_DC;
+  for (int dc = 0; dc < ndc; ++dc) {
+    double S[KB_DC], g2[KB_DC];
+#pragma unroll
+    for (int dd = 0; dd < KB_DC; ++dd) S[dd] = g2[dd] = 0.0;
+
+    for (int rc = rc_start + strip; rc < p.nrc; rc += p.strips) {
+      const int i0 = rc * KB_ROWS;
+      __syncthreads();
+      for (int idx = t; idx < KB_ROWS * D; idx += KB_THREADS) {
+        const int rr = idx / D, d = idx - rr * D;
+        double v = 0.0;
+        if (i0 + rr < p.n1) {
+          v = p.X1[static_cast<long>(i0 + rr) * p.ldx1 + d];
+          if (!linear) v /= ellv[d];
+        }
+        X1s[rr * D + d] = v;
+      }
+      double hreg[KB_RT];
+      if (GPR) {
+        // aa[rr] = sum_o a[i][o] a[j][o], staged in chunks of KB_DY outputs
+#pragma unroll
+        for (int rr = 0; rr < KB_RT; ++rr) hreg[rr] = 0.0;
+        for (int o0 = 0; o0 < p.dy; o0 += KB_DY) {
+          __syncthreads();
+          for (int idx = t; idx < KB_COLS * KB_DY; idx += KB_THREADS) {
+            const int cc = idx / KB_DY, o = idx - cc * KB_DY;
+            acol[idx] = (c0 + cc < p.n2 && o0 + o < p.dy) ? p.a[static_cast<long>(c0 + cc) * p.lda + o0 + o] : 0.0;
+          }
+          for (int idx = t; idx < KB_ROWS * KB_DY; idx += KB_THREADS) {
+            const int rr = idx / KB_DY, o = idx - rr * KB_DY;
+            arow[idx] = (i0 + rr < p.n1 && o0 + o < p.dy) ? p.a[static_cast<long>(i0 + rr) * p.lda + o0 + o] : 0.0;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int o = 0; o < KB_DY; ++o) {
+            const double aj = acol[c * KB_DY + o];
+#pragma unroll
+            for (int rr = 0; rr < KB_RT; ++rr) hreg[rr] += arow[(half * KB_RT + rr) * KB_DY + o] * aj;
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---- phase A: scaled squared distances of this thread's KB_RT rows against its column ----
+      double r2[KB_RT];
+#pragma unroll
+      for (int rr = 0; rr < KB_RT; ++rr) r2[rr] = 0.0;
+      if (!linear) {
+        for (int d = 0; d < D; ++d) {
+          const double x2d = X2s[d * KB_COLS + c];
+#pragma unroll
+          for (int rr = 0; rr < KB_RT; ++rr) {
+            const double diff = X1s[(half * KB_RT + rr) * D + d] - x2d;
+            r2[rr] += diff * diff;
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < KB_RT; ++rr) {
+        const int i = i0 + half * KB_RT + rr;
+        bool valid = jvalid && i < p.n1;
+        double g = 0.0;
+        if (GPR) {
+          valid = valid && i >= j;
+          if (valid) {
+            const bool same_blk = (i / NB) == (j / NB);
+            const double kinv = same_blk ? p.kd[static_cast<long>(i) * NB + (j - (j / NB) * NB)]
+                                         : __ldcs(&p.Kinv[static_cast<long>(i) * p.ldk + j]);
+            const double w = 0.5 * (static_cast<double>(p.dy) * kinv - hreg[rr]);
+            if (i == j) {
+              if (dc == 0) gn += w;
+              g = w;
+            } else {
+              g = 2.0 * w;
+            }
+          }
+        } else if (valid) {
+          g = p.g_trans ? p.G[static_cast<long>(j) * p.ldg + i] : __ldcs(&p.G[static_cast<long>(i) * p.ldg + j]);
+        }
+        double h = 0.0;
+        if (valid) {
+          if (linear) {
+            h = g;
+          } else {
+            double kbase, fac1;
+            kern_base_fac(p.kind, r2[rr], kbase, fac1);
+            if (dc == 0) sK += g * kbase;
+            h = g * fac1 * sig2;
+          }
+        }
+        hreg[rr] = h;
+      }
+
+      // ---- phase B: accumulate this chunk of feature dimensions -------------------------------------
+#pragma unroll
+      for (int dd = 0; dd < KB_DC; ++dd) {
+        const int d = dc * KB_DC + dd;
+        if (d < D) {
+          const double x2d = X2s[d * KB_COLS + c];
+#pragma unroll
+          for (int rr = 0; rr < KB_RT; ++rr) {
+            const double x1d = X1s[(half * KB_RT + rr) * D + d];
+            if (linear) {
+              g2[dd] += hreg[rr] * x1d;
+            } else {
+              const double diff = x1d - x2d;
+              const double u = hreg[rr] * diff;
+              g2[dd] += u;
+              S[dd] += u * diff;
+            }
+          }
+        }
+      }
+    }  // row chunks
+
+    // ---- flush this feature chunk: S -> per-CTA partial, g2 -> per-strip partial ---------------------
+#pragma unroll
+    for (int dd = 0; dd < KB_DC; ++dd) {
+      const int d = dc * KB_DC + dd;
+      if (d >= D) break;  // uniform across the block
+      double s = linear ? g2[dd] * X2s[d * KB_COLS + c] : S[dd];
+      s = block_sum(s, red);
+      if (t == 0) p.part_h[static_cast<long>(cta) * (D + 2) + d] = s;
+      if (p.part_g2) {
+        __syncthreads();
+        comb[half * KB_COLS + c] = g2[dd];
+        __syncthreads();
+        if (half == 0 && jvalid)
+          p.part_g2[(static_cast<long>(strip) * p.n2 + j) * D + d] = comb[c] + comb[KB_COLS + c];
+      }
+    }
+  }
+  sK = block_sum(sK, red);
+  if (t == 0) p.part_h[static_cast<long>(cta) * (D + 2) + D] = sK;
+  gn = block_sum(gn, red);
+  if (t == 0) p.part_h[static_cast<long>(cta) * (D + 2) + D + 1] = gn;
+}
+
+// Final deterministic reduction of the per-CTA partials and scaling to gradients w.r.t. the kernel's own
+// (transformed) hyper-parameters ell, sigma2 (the exp-transform chain rule is left to torch autograd,
+// gptorch/param.py:35).
+__global__ void kbwd_finalize_kernel(int kind, int D, int ell_len, const double* __restrict__ ell, int ncta,
+                                     const double* __restrict__ part_h, int strips, int n2,
+                                     const double* __restrict__ part_g2, double* __restrict__ g_ell,
+                                     double* __restrict__ g_sigma2, double* __restrict__ g_noise,
+                                     double* __restrict__ gX2) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool linear = kind == KERN_LINEAR;
+  if (gid < D + 2) {
+    double s = 0.0;
+    for (int cta = 0; cta < ncta; ++cta) s += part_h[static_cast<long>(cta) * (D + 2) + gid];
+    if (gid < D) {
+      if (linear) {
+        g_ell[gid] = s;
+      } else if (ell_len == D) {
+        g_ell[gid] = s / ell[gid];
+      } else {
+        // isotropic: handled below by thread D-th? -> accumulate serially here for determinism
+      }
+    } else if (gid == D) {
+      if (g_sigma2) g_sigma2[0] = s;
+    } else {
+      if (g_noise) g_noise[0] = s;
+    }
+  }
+  if (gid == 0 && !linear && ell_len == 1) {
+    double tot = 0.0;
+    for (int d = 0; d < D; ++d) {
+      double s = 0.0;
+      for (int cta = 0; cta < ncta; ++cta) s += part_h[static_cast<long>(cta) * (D + 2) + d];
+      tot += s;
+    }
+    g_ell[0] = tot / ell[0];
+  }
+  if (gX2 != nullptr && part_g2 != nullptr) {
+    const long total = static_cast<long>(n2) * D;
+    for (long idx = gid; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+      const int d = static_cast<int>(idx % D);
+      double s = 0.0;
+      for (int st = 0; st < strips; ++st) s += part_g2[static_cast<long>(st) * total + idx];
+      const double e = ell[ell_len == 1 ? 0 : d];
+      gX2[idx] = linear ? s * e : s / e;
+    }
+  }
+}
+
+static inline size_t kbwd_smem_bytes(int D) {
+  return (static_cast<size_t>(D) * KB_COLS + static_cast<size_t>(KB_ROWS) * D + D + KB_COLS * KB_DY + KB_ROWS * KB_DY +
+          32 + 2 * KB_COLS) * sizeof(double);
+}
+
+static inline void kbwd_grid(int nrows, int ncols, bool lower, int& ncb, int& nrc, int& strips) {
+  ncb = (ncols + KB_COLS - 1) / KB_COLS;
+  nrc = (nrows + KB_ROWS - 1) / KB_ROWS;
+  const int target = 4 * 148;
+  strips = std::max(1, std::min(nrc, (target + ncb - 1) / ncb));
+  (void)lower;
+}
+
+size_t kern_bwd_workspace_bytes(int n1, int n2, int D) {
+  int ncb, nrc, strips;
+  kbwd_grid(n1, n2, false, ncb, nrc, strips);
+  const size_t ncta = static_cast<size_t>(ncb) * strips;
+  return (ncta * (D + 2) + static_cast<size_t>(strips) * n2 * D) * sizeof(double) + 256;
+}
+
+template <bool GPR>
+static int kbwd_launch(KbwdParams& p, int ncb, double* g_ell, double* g_sigma2, double* g_noise, double* gX2,
+                       cudaStream_t stream) {
+  const size_t smem = kbwd_smem_bytes(p.D);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    GPB_CUDA_CHECK(cudaFuncSetAttribute(kern_bwd_kernel<GPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(std::max<size_t>(smem, 64 * 1024))));
+    attr_smem = std::max<size_t>(smem, 64 * 1024);
+  }
+  dim3 grid(ncb, p.strips);
+  kern_bwd_kernel<GPR><<<grid, KB_THREADS, smem, stream>>>(p);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  const int ncta = ncb * p.strips;
+  const long work = std::max<long>(p.D + 2, gX2 ? static_cast<long>(p.n2) * p.D : 0);
+  const int blocks = static_cast<int>(std::min<long>((work + 255) / 256, 1024));
+  kbwd_finalize_kernel<<<blocks, 256, 0, stream>>>(p.kind, p.D, p.ell_len, p.ell, ncta, p.part_h, p.strips, p.n2,
+                                                   gX2 ? p.part_g2 : nullptr, g_ell, g_sigma2, g_noise, gX2);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+int kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+             const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
+             double* g_ell, double* g_sigma2, double* gX2, void* workspace, size_t workspace_bytes,
+             cudaStream_t stream) {
+  if (kind < 0 || kind > KERN_LINEAR) return GPB_ERR_BADARG;
+  if (!X || !G || !ell || !g_ell || D <= 0 || (ell_len != 1 && ell_len != D)) return GPB_ERR_BADARG;
+  if (kind != KERN_LINEAR && !sigma2) return GPB_ERR_BADARG;
+  if (kind == KERN_LINEAR && ell_len != D) return GPB_ERR_BADARG;
+  if (D > KB_DMAX) return GPB_ERR_UNSUPPORTED;
+  KbwdParams p{};
+  p.kind = kind;
+  p.X1 = X; p.n1 = n1; p.ldx1 = ldx;
+  if (X2) { p.X2 = X2; p.n2 = n2; p.ldx2 = ldx2; }
+  else { p.X2 = X; p.n2 = n1; p.ldx2 = ldx; }
+  if (n1 <= 0 || p.n2 <= 0) return GPB_ERR_BADARG;
+  p.D = D; p.ell = ell; p.ell_len = ell_len; p.sigma2 = sigma2;
+  p.G = G; p.ldg = ldg; p.g_trans = g_transposed;
+  int ncb;
+  kbwd_grid(n1, p.n2, false, ncb, p.nrc, p.strips);
+  if (!workspace || workspace_bytes < kern_bwd_workspace_bytes(n1, p.n2, D)) return GPB_ERR_BADARG;
+  p.part_h = static_cast<double*>(workspace);
+  p.part_g2 = gX2 ? p.part_h + static_cast<size_t>(ncb) * p.strips * (D + 2) : nullptr;
+  return kbwd_launch<false>(p, ncb, g_ell, g_sigma2, nullptr, gX2, stream);
+}
+
+size_t gpr_grad_workspace_bytes(int n, int D) {
+  int ncb, nrc, strips;
+  kbwd_grid(n, n, true, ncb, nrc, strips);
+  return static_cast<size_t>(ncb) * strips * (D + 2) * sizeof(double) + 256;
+}
+
+int gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* ell, int ell_len,
+             const double* sigma2, const double* Kinv, long ldk, const double* kdiag_blocks, const double* a,
+             int dy, long lda_a, double* g_ell, double* g_sigma2, double* g_noise, void* workspace,
+             size_t workspace_bytes, cudaStream_t stream) {
+  if (kind < 0 || kind > KERN_LINEAR) return GPB_ERR_BADARG;
+  if (!X || !Kinv || !kdiag_blocks || !a || !ell || !g_ell || D <= 0 || n <= 0 || dy <= 0) return GPB_ERR_BADARG;
+  if (ell_len != 1 && ell_len != D) return GPB_ERR_BADARG;
+  if (kind != KERN_LINEAR && !sigma2) return GPB_ERR_BADARG;
+  if (D > KB_DMAX) return GPB_ERR_UNSUPPORTED;
+  KbwdParams p{};
+  p.kind = kind;
+  p.X1 = X; p.n1 = n; p.ldx1 = ldx;
+  p.X2 = X; p.n2 = n; p.ldx2 = ldx;
+  p.D = D; p.ell = ell; p.ell_len = ell_len; p.sigma2 = sigma2;
+  p.Kinv = Kinv; p.ldk = ldk; p.kd = kdiag_blocks; p.a = a; p.dy = dy; p.lda = lda_a;
+  int ncb;
+  kbwd_grid(n, n, true, ncb, p.nrc, p.strips);
+  if (!workspace || workspace_bytes < gpr_grad_workspace_bytes(n, D)) return GPB_ERR_BADARG;
+  p.part_h = static_cast<double*>(workspace);
+  p.part_g2 = nullptr;
+  return kbwd_launch<true>(p, ncb, g_ell, g_sigma2, g_noise, nullptr, stream);
+}
+
+}  // namespace gpb

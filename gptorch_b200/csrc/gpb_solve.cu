@@ -1,0 +1,279 @@
+// gpb_solve.cu -- HBM-bound pieces of the hot path: triangular solves with few right-hand sides,
+// log-determinant / sum-of-squares reduction, and small matrix utilities.
+//
+// Reference call sites: functions.trtrs (gptorch/functions.py:71-76) as used for alpha = L^-1 (y - m)
+// (gptorch/models/gpr.py:62, :106), functions.lt_log_determinant (gptorch/functions.py:61-68), the jitter
+// add of functions.jit_op (:36) and the zero upper triangle torch.cholesky returns (:47).
+//
+// trsv: ONE launch per (<=4 right-hand sides).  CTA `i` owns the 128-row block i of the solution; it streams
+// the tiles L[i][j] (forward) or L[j][i] (transposed) exactly once -- 4 n^2 bytes in total, the roofline of
+// the operation -- and waits on a per-block ready flag published by the CTA that owns block j.  Row blocks are
+// handed out by an atomic ticket so a waiting CTA only ever depends on CTAs that are already running.
+#include "gpb_common.cuh"
+#include <algorithm>
+
+namespace gpb {
+
+constexpr int TRSV_THREADS = 256;
+
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_i32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// y[r] (+)= sum_c T[r][c] * x[c][q]  for a 128 x 128 row-major tile T (ld), rows split over 8 warps, lanes
+// along c (coalesced).  sign = -1 accumulates into accs (accs[r][q] -= ...), mode_out writes result to out.
+template <int KR>
+__device__ __forceinline__ void tile_rowdot(const double* __restrict__ T, long ld, int rows_valid, int cols_valid,
+                                            const double (*xs)[KR], double (*accs)[KR], bool subtract,
+                                            double (*outs)[KR]) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 2
+  for (int rr = 0; rr < 16; ++rr) {
+    const int r = w * 16 + rr;
+    double part[KR];
+#pragma unroll
+    for (int q = 0; q < KR; ++q) part[q] = 0.0;
+    if (r < rows_valid) {
+      const double* trow = T + static_cast<long>(r) * ld;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int c = lane + 32 * m;
+        const double v = (c < cols_valid) ? __ldcs(trow + c) : 0.0;
+#pragma unroll
+        for (int q = 0; q < KR; ++q) part[q] += v * xs[c][q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < KR; ++q) part[q] = warp_sum(part[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < KR; ++q) {
+        if (subtract) accs[r][q] -= part[q];
+        else outs[r][q] = part[q];
+      }
+    }
+  }
+}
+
+template <int KR>
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_kernel(const double* __restrict__ L, long ldl, int n,
+                                                                const double* __restrict__ dinv, double* B, long ldb,
+                                                                int col0, int kr, int* flags, int* ticket) {
+  __shared__ int s_id;
+  __shared__ double xs[NB][KR];
+  __shared__ double accs[NB][KR];
+  __shared__ double outs[NB][KR];
+  const int t = threadIdx.x;
+  if (t == 0) s_id = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int i = s_id;
+  const int r0 = i * NB;
+  const int nbi = min(NB, n - r0);
+  for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
+    const int r = idx / KR, q = idx % KR;
+    accs[r][q] = (r < nbi && q < kr) ? B[static_cast<long>(r0 + r) * ldb + col0 + q] : 0.0;
+  }
+  for (int j = 0; j < i; ++j) {
+    if (t == 0) {
+      while (ld_acquire_i32(&flags[j]) == 0) { __nanosleep(20); }
+    }
+    __syncthreads();
+    for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
+      const int c = idx / KR, q = idx % KR;
+      xs[c][q] = (q < kr) ? __ldcg(&B[static_cast<long>(j * NB + c) * ldb + col0 + q]) : 0.0;
+    }
+    __syncthreads();
+    tile_rowdot<KR>(L + static_cast<long>(r0) * ldl + j * NB, ldl, nbi, NB, xs, accs, true, outs);
+  }
+  __syncthreads();
+  // x_i = Inv_ii * acc   (Inv padded with identity; zeros above the diagonal)
+  for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
+    const int c = idx / KR, q = idx % KR;
+    xs[c][q] = accs[c][q];
+  }
+  __syncthreads();
+  tile_rowdot<KR>(dinv + static_cast<long>(r0) * NB, NB, NB, NB, xs, accs, false, outs);
+  __syncthreads();
+  for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
+    const int r = idx / KR, q = idx % KR;
+    if (r < nbi && q < kr) B[static_cast<long>(r0 + r) * ldb + col0 + q] = outs[r][q];
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) st_release_i32(&flags[i], 1);
+}
+
+// Transposed solve: x_i = Inv_ii^T (b_i - sum_{j>i} L[j][i]^T x_j), blocks processed from the last one.
+template <int KR>
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_kernel(const double* __restrict__ L, long ldl, int n,
+                                                                const double* __restrict__ dinv, double* B, long ldb,
+                                                                int col0, int kr, int* flags, int* ticket) {
+  __shared__ int s_id;
+  __shared__ double xs[NB][KR];
+  __shared__ double accs[NB][KR];
+  __shared__ double part2[2][NB][KR];
+  const int t = threadIdx.x;
+  const int nblk = (n + NB - 1) / NB;
+  if (t == 0) s_id = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int i = nblk - 1 - s_id;
+  const int c0 = i * NB;
+  const int nbi = min(NB, n - c0);
+  const int c = t & 127, half = t >> 7;
+  for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
+    const int r = idx / KR, q = idx % KR;
+    accs[r][q] = (r < nbi && q < kr) ? B[static_cast<long>(c0 + r) * ldb + col0 + q] : 0.0;
+  }
+  for (int j = nblk - 1; j > i; --j) {
+    if (t == 0) {
+      while (ld_acquire_i32(&flags[j]) == 0) { __nanosleep(20); }
+    }
+    __syncthreads();
+    const int nbj = min(NB, n - j * NB);
+    for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
+      const int r = idx / KR, q = idx % KR;
+      xs[r][q] = (r < nbj && q < kr) ? __ldcg(&B[static_cast<long>(j * NB + r) * ldb + col0 + q]) : 0.0;
+    }
+    __syncthreads();
+    double p[KR];
+#pragma unroll
+    for (int q = 0; q < KR; ++q) p[q] = 0.0;
+    const double* tile = L + static_cast<long>(j) * NB * ldl + c0 + c;
+    const int rbeg = half * 64, rend = min(rbeg + 64, nbj);
+    if (c < nbi) {
+#pragma unroll 8
+      for (int r = rbeg; r < rend; ++r) {
+        const double v = __ldcs(tile + static_cast<long>(r) * ldl);
+#pragma unroll
+        for (int q = 0; q < KR; ++q) p[q] += v * xs[r][q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < KR; ++q) part2[half][c][q] = p[q];
+    __syncthreads();
+    if (half == 0) {
+#pragma unroll
+      for (int q = 0; q < KR; ++q) accs[c][q] -= part2[0][c][q] + part2[1][c][q];
+    }
+    // next iteration's first __syncthreads orders these writes before xs/part2 are reused
+  }
+  __syncthreads();
+  // x_i[c] = sum_{r >= c} Inv_ii[r][c] * acc[r]
+  {
+    double p[KR];
+#pragma unroll
+    for (int q = 0; q < KR; ++q) p[q] = 0.0;
+    const double* tile = dinv + static_cast<long>(c0) * NB + c;
+    const int rbeg = half * 64, rend = rbeg + 64;
+#pragma unroll 8
+    for (int r = rbeg; r < rend; ++r) {
+      const double v = tile[r * NB];
+#pragma unroll
+      for (int q = 0; q < KR; ++q) p[q] += v * accs[r][q];
+    }
+#pragma unroll
+    for (int q = 0; q < KR; ++q) part2[half][c][q] = p[q];
+  }
+  __syncthreads();
+  if (half == 0 && c < nbi) {
+    for (int q = 0; q < kr; ++q) B[static_cast<long>(c0 + c) * ldb + col0 + q] = part2[0][c][q] + part2[1][c][q];
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) st_release_i32(&flags[i], 1);
+}
+
+size_t trsv_workspace_bytes(int n) { return (static_cast<size_t>((n + NB - 1) / NB) + 1) * sizeof(int); }
+
+int trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, int k, long ldb, int trans,
+               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (n <= 0 || k <= 0) return GPB_OK;
+  if (!L || !dinv || !B || ldl < n || ldb < k || !workspace || workspace_bytes < trsv_workspace_bytes(n))
+    return GPB_ERR_BADARG;
+  const int nblk = (n + NB - 1) / NB;
+  int* flags = static_cast<int*>(workspace);
+  int* ticket = flags + nblk;
+  for (int col0 = 0; col0 < k; col0 += 4) {
+    const int kr = std::min(4, k - col0);
+    GPB_CUDA_CHECK(cudaMemsetAsync(workspace, 0, trsv_workspace_bytes(n), stream));
+    if (trans == 0) {
+      if (kr == 1) trsv_fwd_kernel<1><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
+      else if (kr == 2) trsv_fwd_kernel<2><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
+      else trsv_fwd_kernel<4><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
+    } else {
+      if (kr == 1) trsv_bwd_kernel<1><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
+      else if (kr == 2) trsv_bwd_kernel<2><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
+      else trsv_bwd_kernel<4><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
+    }
+    GPB_CUDA_CHECK(cudaGetLastError());
+  }
+  return GPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[0] = sum log L_ii ; out[1] = sum V^2.  One CTA, fixed reduction tree => deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) logdet_sumsq_kernel(const double* __restrict__ L, int n, long ldl,
+                                                            const double* __restrict__ V, int k, long ldv,
+                                                            double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += log(L[static_cast<long>(i) * (ldl + 1)]);
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[0] = s;
+  double q = 0.0;
+  if (V != nullptr) {
+    const long total = static_cast<long>(n) * k;
+    for (long idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const long r = idx / k, c = idx - r * k;
+      const double v = V[r * ldv + c];
+      q += v * v;
+    }
+  }
+  q = block_sum(q, scratch);
+  if (threadIdx.x == 0) out[1] = q;
+}
+
+int logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out,
+                 cudaStream_t stream) {
+  if (!L || !out || n < 0) return GPB_ERR_BADARG;
+  logdet_sumsq_kernel<<<1, 1024, 0, stream>>>(L, n, ldl, V, k, ldv, out);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+__global__ void tri_zero_upper_kernel(double* __restrict__ A, int n, long lda) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c < n && c > r) A[static_cast<long>(r) * lda + c] = 0.0;
+}
+
+int tri_zero_upper(double* A, int n, long lda, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  if (!A || lda < n) return GPB_ERR_BADARG;
+  dim3 grid((n + 255) / 256, n);
+  tri_zero_upper_kernel<<<grid, 256, 0, stream>>>(A, n, lda);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+__global__ void add_diag_kernel(double* __restrict__ A, int n, long lda, const double* __restrict__ value,
+                                double host_value) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[static_cast<long>(i) * (lda + 1)] += value ? *value : host_value;
+}
+
+int add_diag(double* A, int n, long lda, const double* value, double host_value, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  if (!A || lda < n) return GPB_ERR_BADARG;
+  add_diag_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A, n, lda, value, host_value);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+}  // namespace gpb

@@ -1,0 +1,158 @@
+/* gpb200.h -- C ABI of libgpb200.so, the B200 (sm_100a) implementation of gptorch's dense-GP hot path.
+ *
+ * The reference (cics-nd/gptorch v0.3.2) has no FFI: its hot path is Python calling torch ops.  Each entry
+ * point below names the reference call site it replaces (file:line under the reference tree); the
+ * reference-side binding a maintainer would add is the ctypes stub in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every matrix is fp64, row-major, on the current CUDA device; `ld*` are leading dimensions in elements;
+ *   - pointers are plain device pointers, `stream` is a cudaStream_t passed as void*;
+ *   - hyper-parameters (length scales, variances) are DEVICE pointers so a call never synchronises;
+ *   - the library never allocates or frees: workspaces are supplied by the caller (see *_workspace_bytes);
+ *   - return value: 0 = launched, <0 = rejected (GPB_ERR_*); numerical status (LAPACK-style `info`) is
+ *     written to a device int by the kernels and read by the caller when it chooses to synchronise;
+ *   - matrices handed to the GEMM-based entry points (potrf/potri/trsm/gemm) need a 16-byte aligned base
+ *     and an even leading dimension (TMA requirement); GPB_ERR_ALIGN is returned otherwise.
+ */
+#ifndef GPB200_H_
+#define GPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_OK 0
+#define GPB_ERR_BADARG (-1)
+#define GPB_ERR_ALIGN (-2)
+#define GPB_ERR_CUDA (-3)
+#define GPB_ERR_DRIVER (-4)
+#define GPB_ERR_UNSUPPORTED (-5)
+
+/* Covariance families.  Reference: gptorch/kernels.py Rbf :215-222, Exp/Matern12 :182-194,
+ * Matern32 :197-201, Matern52 :204-212, Linear :238-265. */
+enum gpb_kernel_kind {
+  GPB_KERN_RBF = 0,
+  GPB_KERN_EXP = 1,      /* == Matern12 */
+  GPB_KERN_MATERN32 = 2,
+  GPB_KERN_MATERN52 = 3,
+  GPB_KERN_LINEAR = 4
+};
+
+/* Which part of a symmetric output to produce. */
+enum gpb_fill { GPB_FILL_FULL = 0, GPB_FILL_LOWER = 1 };
+
+int gpb_version(void);
+/* Human-readable description of the last error on the calling thread (never NULL). */
+const char* gpb_last_error(void);
+/* ABI block size: diagonal-block workspaces (`dinv`, `kdiag_blocks`) are ceil(n/128)*128 rows of 128 doubles. */
+int gpb_block_size(void);
+
+/* ---- covariance construction ---------------------------------------------------------------------------
+ * K[i][j] = k(X[i,:], X2[j,:]).  Replaces Kernel.K(X, X2) (gptorch/kernels.py:189,198,205,220,258) with its
+ * callees Stationary.squared_dist/dist (:149-172) and util.squared_distance (gptorch/util.py:73-88):
+ * scaled squared distance by the expansion |a|^2+|b|^2-2ab (the a.b term on FP64 DMMA), clamp at 0, the
+ * kernel non-linearity, times the variance.  X2 == NULL means X2 = X.
+ *   ell:     device, length ell_len (1 = isotropic, D = ARD); for GPB_KERN_LINEAR it is the per-dimension
+ *            variance vector v (ell_len == D) and `sigma2` is ignored (may be NULL).
+ *   noise:   optional device scalar added to the diagonal when X2 == NULL (GPR._compute_kyy,
+ *            gptorch/models/gpr.py:69-86, without the dense N x N diagonal temporary).
+ *   fill:    GPB_FILL_LOWER skips tiles strictly above the diagonal (only valid when X2 == NULL). */
+int gpb_kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                 const double* ell, int ell_len, const double* sigma2, const double* noise, int fill,
+                 double* K, long ldk, void* stream);
+
+/* Bytes of scratch needed by gpb_kern_bwd for the given problem. */
+size_t gpb_kern_bwd_workspace_bytes(int n1, int n2, int D);
+
+/* Backward of gpb_kern_fwd for an upstream gradient G = dLoss/dK (n1 x n2, ldg).  Replaces torch autograd
+ * through the composite ops of gptorch/kernels.py and gptorch/util.py:82-88 (gradient passes the r^2 clamp
+ * unchanged; for Exp/Matern the sqrt clamp at 1e-40 zeroes it, gptorch/kernels.py:171-172).
+ *   g_ell:    out, ell_len doubles: dLoss/d ell  (for LINEAR: dLoss/d v)
+ *   g_sigma2: out, 1 double (ignored for LINEAR; may be NULL)
+ *   gX2:      optional out, n2 x D (ld = D): dLoss/dX2 treating X as constant.  (The gradient w.r.t. the first
+ *             argument is obtained by calling again with the arguments swapped and g_transposed = 1.)
+ *   g_transposed: G is stored n2 x n1 (element (i,j) at G[j*ldg + i]). */
+int gpb_kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                 const double* ell, int ell_len, const double* sigma2, const double* G, long ldg,
+                 int g_transposed, double* g_ell, double* g_sigma2, double* gX2, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* Kdiag for the non-stationary kernel (Linear.Kdiag, gptorch/kernels.py:264-265): out[i] = sum_d v_d x_id^2.
+ * Stationary kernels return the variance broadcast (gptorch/kernels.py:174-179) and need no kernel. */
+int gpb_linear_kdiag(const double* X, int n, long ldx, int D, const double* v, double* out, void* stream);
+
+/* ---- Cholesky ------------------------------------------------------------------------------------------
+ * In-place lower Cholesky of the symmetric matrix whose LOWER triangle is stored in A (n x n, lda).
+ * Replaces torch.cholesky behind functions.cholesky (gptorch/functions.py:46-47).  The strictly upper
+ * triangle of A is scratch afterwards (gpb_tri_zero_upper restores the reference's zero upper triangle).
+ *   dinv:  out workspace, ceil(n/128)*128 x 128 doubles: inverses of the 128 x 128 diagonal blocks of L
+ *          (used by the solves and by gpb_potri_lower).
+ *   info:  device int, must be zeroed by the caller; set to the 1-based index of the first non-positive
+ *          pivot (LAPACK potrf semantics: the factorisation "failed" and jit_op must add jitter,
+ *          gptorch/functions.py:28-43). */
+int gpb_potrf_lower(double* A, int n, long lda, double* dinv, int* info, void* stream);
+
+/* Inverses of the diagonal 128-blocks of an existing lower factor L (for callers that did not run potrf). */
+int gpb_tri_diag_inverse(const double* L, int n, long ldl, double* dinv, void* stream);
+
+size_t gpb_potri_workspace_bytes(int n);
+/* Given L (lower triangle of A, with `dinv` from potrf) compute (L L^T)^-1.  Replaces
+ * functions.cholesky_inverse (gptorch/functions.py:50-54) and, inside the fused GPR backward, autograd's
+ * CholeskyBackward0.  On return: strictly-lower 128-blocks of A hold the inverse; the diagonal 128-blocks are
+ * in kdiag_blocks (ceil(n/128)*128 x 128, symmetric, full); the upper triangle of A is scratch. */
+int gpb_potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* Expand the blocked result of gpb_potri_lower into a full symmetric n x n matrix `out` (ldo). */
+int gpb_potri_assemble(const double* A, int n, long lda, const double* kdiag_blocks, double* out, long ldo,
+                       void* stream);
+
+/* Zero the strictly upper triangle (torch.cholesky returns a clean lower factor). */
+int gpb_tri_zero_upper(double* A, int n, long lda, void* stream);
+/* A[i][i] += *value (value: device scalar) or += host_value when value == NULL (jitter, functions.py:36). */
+int gpb_add_diag(double* A, int n, long lda, const double* value, double host_value, void* stream);
+
+/* ---- triangular solves and log-determinant ---------------------------------------------------------------
+ * B <- L^-1 B (trans = 0) or L^-T B (trans = 1), L lower n x n, B n x k row-major (ldb), in place.
+ * Replaces functions.trtrs (gptorch/functions.py:71-76) -- without torch.triangular_solve's clone of L.
+ * `dinv` are the diagonal-block inverses of L (from potrf or gpb_tri_diag_inverse).  One launch per group
+ * of <= 4 right-hand sides streams L exactly once; `workspace` holds the per-block ready flags. */
+size_t gpb_trsv_workspace_bytes(int n);
+int gpb_trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, int k, long ldb, int trans,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* Right-side solve on a row-panel: X <- X L^-T, X m x n row-major (ldx), L lower n x n.  This is the layout
+ * the sparse models use for A^T = Kfu L^-T (gptorch/models/sparse_gpr.py:132,360). */
+int gpb_trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* X, int m, long ldx,
+                      void* stream);
+
+/* out[0] = sum_i log L[i][i]  (functions.lt_log_determinant, gptorch/functions.py:61-68);
+ * out[1] = sum of squares of the n x k matrix V (ldv) if V != NULL (the -1/2 sum alpha^2 term,
+ * gptorch/models/gpr.py:66).  Deterministic (fixed reduction order). */
+int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out,
+                     void* stream);
+
+/* ---- GEMM ------------------------------------------------------------------------------------------------
+ * C = alpha * op(A) op(B) + beta * C on the FP64 DMMA engine.  mode: 0 = A B^T (A: m x k, B: n x k),
+ * 1 = A^T B (A: k x m, B: k x n), 2 = A B (A: m x k, B: k x n).  lower_only skips tiles above the diagonal
+ * (SYRK).  Replaces the `@` products of gptorch/models/sparse_gpr.py:133,137,176,183,360-370. */
+int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,
+             double beta, double* C, long ldc, int lower_only, void* stream);
+
+/* ---- fused GPR gradient ------------------------------------------------------------------------------------
+ * Given Kinv in the blocked form left by gpb_potri_lower and a = Ky^-1 (y - m) (n x dy, lda_a), reduce
+ *    W = 1/2 (dy * Kinv - a a^T)            (dLoss/dKy; gptorch/models/gpr.py:47-67)
+ * against dK/d(ell, sigma2) without materialising W or K:  g_ell[d] = sum_ij W_ij dK_ij/d ell_d,
+ * g_sigma2 = sum_ij W_ij K_ij / sigma2, g_noise = tr W.  Replaces the autograd backward of
+ * kernels.K + _compute_kyy + cholesky + trtrs. */
+size_t gpb_gpr_grad_workspace_bytes(int n, int D);
+int gpb_gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* ell, int ell_len,
+                 const double* sigma2, const double* Kinv, long ldk, const double* kdiag_blocks,
+                 const double* a, int dy, long lda_a, double* g_ell, double* g_sigma2, double* g_noise,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H_ */
