@@ -1,0 +1,371 @@
+"""torch.autograd.Function nodes over the native library.
+
+The reference has no custom autograd nodes: gradients come from torch autograd through composite ops
+(gptorch/functions.py:1-5 says otherwise but none exist).  Here every forward AND backward is a call (or a
+short sequence of calls) into libgpb200.so; the backward formulas are the closed forms verified against the
+reference's autograd in SURVEY.md section 10.
+"""
+import math
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _native as nv
+
+TRSV_MAX_RHS = 32  # up to this many right-hand sides use the streaming trsv kernel, beyond it the GEMM path
+
+
+class Factor:
+    """A lower Cholesky factor as the native library keeps it: an (n, ld) buffer whose lower triangle is L,
+    plus the inverses of its 128x128 diagonal blocks."""
+
+    __slots__ = ("buf", "ld", "n", "dinv")
+
+    def __init__(self, buf, ld, n, dinv):
+        self.buf, self.ld, self.n, self.dinv = buf, ld, n, dinv
+
+
+def _dinv_of(L):
+    """Diagonal-block inverses of a lower-triangular tensor, reusing the ones cached by functions.cholesky()."""
+    dinv = getattr(L, "_gpb_dinv", None)
+    if dinv is not None and dinv.shape[0] >= L.shape[0] and dinv.device == L.device:
+        return dinv
+    return nv.tri_diag_inverse(nv._c(L))
+
+
+def _tinv(L, dinv):
+    """T = L^-T as a dense upper-triangular tensor (n x n view of a TMA-aligned buffer)."""
+    n = L.shape[0]
+    buf, ld = nv.sym_buffer_from(L)
+    nv.trtri_upper_(buf, ld, dinv)
+    T = buf[:, :n]
+    T.triu_()  # the strictly-lower off-diagonal blocks still hold L
+    return T
+
+
+# ------------------------------------------------------------------------------------------------------
+# covariance
+# ------------------------------------------------------------------------------------------------------
+class KernelFn(Function):
+    """K(X, X2) for the stationary kernels and Linear (gptorch/kernels.py:182-265); with `noise` (and X2 None)
+    it is Ky = K(X) + noise I of GPR._compute_kyy (gptorch/models/gpr.py:69-86)."""
+
+    @staticmethod
+    def forward(ctx, kind, X, X2, ell, sigma2, noise=None):
+        ctx.kind = kind
+        ctx.save_for_backward(X, X2, ell, sigma2)
+        return nv.kern_fwd(kind, X, X2, ell, sigma2, noise=noise if X2 is None else None)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        X, X2, ell, sigma2 = ctx.saved_tensors
+        kind = ctx.kind
+        need_x, need_x2 = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        sym = X2 is None
+        G = nv._c(G)
+        g_ell, g_s2, g_col = nv.kern_bwd(kind, X, X2, ell, sigma2, G, need_x2 or (sym and need_x))
+        gX = gX2 = None
+        if need_x:
+            _, _, g_row = nv.kern_bwd(kind, X if sym else X2, X, ell, sigma2, G, True, g_transposed=True)
+            gX = g_row + g_col if sym else g_row
+        if need_x2 and not sym:
+            gX2 = g_col
+        g_ell = g_ell.reshape(ell.shape) if ctx.needs_input_grad[3] else None
+        g_s2 = g_s2.reshape(sigma2.shape) if (sigma2 is not None and ctx.needs_input_grad[4]) else None
+        g_noise = G.diagonal().sum().reshape(1) if (len(ctx.needs_input_grad) > 5 and ctx.needs_input_grad[5]) else None
+        return None, gX, gX2, g_ell, g_s2, g_noise
+
+
+# ------------------------------------------------------------------------------------------------------
+# Cholesky and solves
+# ------------------------------------------------------------------------------------------------------
+def _raise_not_pd(info):
+    raise torch.linalg.LinAlgError(
+        "gpb_potrf_lower: the leading minor of order %d is not positive-definite (the input might not be "
+        "positive-definite)." % info)
+
+
+class CholeskyFn(Function):
+    """Lower Cholesky (torch.cholesky at gptorch/functions.py:47).  Raises LinAlgError (a RuntimeError, which
+    is what jit_op's retry loop catches, gptorch/functions.py:38) on a non-positive pivot."""
+
+    @staticmethod
+    def forward(ctx, A):
+        n = A.shape[0]
+        buf, ld = nv.sym_buffer_from(A)
+        dinv, info = nv.potrf_(buf, ld)
+        status = int(info.item())  # the one host sync of a factorisation (SURVEY 7 "hard parts")
+        if status != 0:
+            _raise_not_pd(status)
+        nv.tri_zero_upper_(buf, ld)
+        L = buf[:, :n]
+        ctx.save_for_backward(L, dinv)
+        ctx.mark_non_differentiable(dinv)
+        return L, dinv
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gL, _g_dinv):
+        L, dinv = ctx.saved_tensors
+        T = _tinv(L, dinv)
+        P = nv.gemm(nv.GEMM_TN, L, nv._c(gL))  # L^T gL
+        P.tril_()
+        P.diagonal().mul_(0.5)
+        W1 = nv.gemm(nv.GEMM_NT, P, T)         # Phi T^T
+        S = nv.gemm(nv.GEMM_NN, T, W1)         # T Phi T^T = L^-T Phi L^-1
+        return 0.5 * (S + S.t())
+
+
+class TrsvFn(Function):
+    """x = L^-1 b (trans=False) or L^-T b (trans=True) for few right-hand sides (functions.trtrs with
+    b = y - m, gptorch/models/gpr.py:62).  L is streamed once per group of 4 columns."""
+
+    @staticmethod
+    def forward(ctx, b, L, dinv, trans):
+        x = nv._c(b).clone()
+        nv.trsv_(nv._c(L), dinv, x, trans)
+        ctx.trans = trans
+        ctx.save_for_backward(L, dinv, x)
+        return x
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        L, dinv, x = ctx.saved_tensors
+        gb = nv._c(g).clone()
+        nv.trsv_(nv._c(L), dinv, gb, not ctx.trans)
+        gL = None
+        if ctx.needs_input_grad[1]:
+            if ctx.trans:   # x = L^-T b:  dL = -tril(x gb^T)
+                gL = nv.gemm(nv.GEMM_NT, x, gb, alpha=-1.0)
+            else:           # x = L^-1 b:  dL = -tril(gb x^T)
+                gL = nv.gemm(nv.GEMM_NT, gb, x, alpha=-1.0)
+            gL.tril_()
+        return gb, gL, None, None
+
+
+class TrsmRightFn(Function):
+    """Out = X L^-T for a row panel X (m x n): the layout the sparse models use for A^T = Kfu L^-T
+    (gptorch/models/sparse_gpr.py:132, :360 compute the transpose, L^-1 Kuf)."""
+
+    @staticmethod
+    def forward(ctx, X, L, dinv):
+        m, n = X.shape
+        buf, ld = nv._aligned_empty(m, n, X.device)
+        buf[:, :n].copy_(X)
+        nv.trsm_right_lt_(nv._gemm_operand(L), dinv, buf, ld)
+        out = buf[:, :n]
+        ctx.save_for_backward(L, dinv, out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        L, dinv, out = ctx.saved_tensors
+        T = _tinv(L, dinv)
+        G = nv._c(G)
+        gX = nv.gemm(nv.GEMM_NT, G, T) if ctx.needs_input_grad[0] else None   # G L^-1 = G T^T
+        gL = None
+        if ctx.needs_input_grad[1]:
+            Q = nv.gemm(nv.GEMM_TN, G, out)                  # G^T Out
+            gL = nv.gemm(nv.GEMM_NN, T, Q, alpha=-1.0)       # -L^-T G^T Out
+            gL.tril_()
+        return gX, gL, None
+
+
+class LogDetFn(Function):
+    """sum(log(diag(L)))  (functions.lt_log_determinant, gptorch/functions.py:61-68)."""
+
+    @staticmethod
+    def forward(ctx, L):
+        ctx.save_for_backward(L)
+        return nv.logdet_sumsq(nv._c(L))[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (L,) = ctx.saved_tensors
+        return torch.diag_embed(g / L.diagonal())
+
+
+class GemmFn(Function):
+    """C = A B^T (NT), A^T B (TN) or A B (NN) on the DMMA engine, differentiable in A and B."""
+
+    @staticmethod
+    def forward(ctx, mode, A, B):
+        ctx.mode = mode
+        ctx.save_for_backward(A, B)
+        return nv.gemm(mode, A, B)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        A, B = ctx.saved_tensors
+        G = nv._c(G)
+        need_a, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gA = gB = None
+        if ctx.mode == nv.GEMM_NT:      # C = A B^T
+            if need_a: gA = nv.gemm(nv.GEMM_NN, G, B)
+            if need_b: gB = nv.gemm(nv.GEMM_TN, G, A)
+        elif ctx.mode == nv.GEMM_TN:    # C = A^T B
+            if need_a: gA = nv.gemm(nv.GEMM_NT, B, G)
+            if need_b: gB = nv.gemm(nv.GEMM_NN, A, G)
+        else:                           # C = A B
+            if need_a: gA = nv.gemm(nv.GEMM_NT, G, B)
+            if need_b: gB = nv.gemm(nv.GEMM_TN, A, G)
+        return None, gA, gB
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused GPR log marginal likelihood
+# ------------------------------------------------------------------------------------------------------
+JITTER_TRIES = 10  # gptorch/functions.py:21
+
+
+class GPRLogLikFn(Function):
+    """GPR.log_likelihood (gptorch/models/gpr.py:47-67) as one node.
+
+    forward : Ky = K(X) + noise I (lower tiles only) -> potrf (same jitter schedule as functions.jit_op,
+              gptorch/functions.py:28-43) -> alpha = L^-1 resid -> -1/2 |alpha|^2 - dy sum log L_ii - const.
+    backward: a = L^-T alpha ; Kinv = potri(L) in place ; W = 1/2 (dy Kinv - a a^T) reduced against
+              dK/d(ell, sigma2) on the fly ; d/d noise = tr W ; d/d resid = -a.       
+    One N^2 buffer in total; N^3/3 + 2N^3/3 flops.
+    """
+
+    @staticmethod
+    def forward(ctx, kind, X, resid, ell, sigma2, noise):
+        n, dy = resid.shape
+        X = nv._c(X)
+        buf, ld = nv._aligned_empty(n, n, X.device)
+        dinv = None
+        for attempt in range(JITTER_TRIES + 1):
+            with nv.phase("kern_fwd"):
+                nv.kern_fwd(kind, X, None, ell, sigma2, noise=noise, lower=True, out=buf, ldk=ld)
+            if attempt > 0:
+                nv.add_diag_(buf, ld, 10.0 ** (-JITTER_TRIES + attempt - 1))
+            with nv.phase("potrf"):
+                dinv, info = nv.potrf_(buf, ld)
+            if int(info.item()) == 0:
+                break
+        else:
+            raise RuntimeError("Max tries exceeded.")
+        with nv.phase("solve_logdet"):
+            alpha = nv._c(resid).clone()
+            nv.trsv_(buf, dinv, alpha, False)
+            red = nv.logdet_sumsq(buf, alpha)
+        loglik = (-0.5 * red[1] - dy * red[0] - 0.5 * dy * n * math.log(2.0 * math.pi)).reshape(1)
+        ctx.kind, ctx.ld, ctx.used = kind, ld, False
+        ctx.save_for_backward(X, ell, sigma2, buf, dinv, alpha)
+        return loglik
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        if ctx.used:
+            raise RuntimeError("GPRLogLikFn: the factor buffer was consumed by a previous backward pass")
+        ctx.used = True
+        X, ell, sigma2, buf, dinv, alpha = ctx.saved_tensors
+        dy = alpha.shape[1]
+        with nv.phase("solve_logdet"):
+            a = alpha.clone()
+            nv.trsv_(buf, dinv, a, True)                 # a = Ky^-1 resid
+        with nv.phase("potri"):
+            kd = nv.potri_(buf, ctx.ld, dinv)            # Kinv, in place (L is gone after this)
+        with nv.phase("gpr_grad"):
+            g_ell, g_s2, g_noise = nv.gpr_grad(ctx.kind, X, ell, sigma2, buf, ctx.ld, kd, a)
+        g = g.reshape(())
+        # the native reduction returns d(-loglik)/d theta; the node's output is +loglik
+        out_ell = (-g) * g_ell.reshape(ell.shape) if ctx.needs_input_grad[3] else None
+        out_s2 = (-g) * g_s2.reshape(sigma2.shape) if (sigma2 is not None and ctx.needs_input_grad[4]) else None
+        out_noise = (-g) * g_noise.reshape(-1) if ctx.needs_input_grad[5] else None
+        out_resid = (-g) * a if ctx.needs_input_grad[2] else None
+        return None, None, out_resid, out_ell, out_s2, out_noise
+
+
+# ------------------------------------------------------------------------------------------------------
+# VFE sufficient statistics, streamed over row chunks of X
+# ------------------------------------------------------------------------------------------------------
+class VfeStatsFn(Function):
+    """(A A^T, A Y) with A = L^-1 Kuf (gptorch/models/sparse_gpr.py:127-137) without ever holding Kuf.
+
+    Rows of X are processed in chunks: Kfu_c = K(X_c, Z) -> At_c = Kfu_c L^-T -> AA += At_c^T At_c,
+    AY += At_c^T Y_c (the reference's order of operations: solve first, then the Gram product).  backward
+    re-streams the chunks: G_c = At_c (S L^-1) + Y_c (L^-T gAY)^T with S = gAA + gAA^T, reduced against
+    dK/d(ell, sigma2, Z) by gpb_kern_bwd.  With torch.distributed initialised and `group` given, rows are this
+    rank's shard and the two statistics / the streamed gradients are all-reduced.
+    """
+
+    @staticmethod
+    def forward(ctx, kind, X, Y, Z, ell, sigma2, L, chunk, group):
+        X, Y, Z = nv._c(X), nv._c(Y), nv._c(Z)
+        Lc = nv._gemm_operand(L)
+        dinv = _dinv_of(L)
+        n, m, dy = X.shape[0], Z.shape[0], Y.shape[1]
+        AA, ldaa = nv._aligned_empty(m, m, X.device)
+        AA.zero_()
+        AY, _ = nv._aligned_empty(m, dy, X.device)
+        AY.zero_()
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            At, ldat = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, Lc, dinv)
+            nv.gemm(nv.GEMM_TN, At, At, beta=1.0, C=AA[:, :m], lower_only=True)
+            nv.gemm(nv.GEMM_TN, At, Y[s:e], beta=1.0, C=AY[:, :dy])
+        AAf = AA[:, :m]
+        AAf = torch.tril(AAf) + torch.tril(AAf, -1).t()
+        AYf = AY[:, :dy].contiguous()
+        # sum_i k(x_i, x_i) = n * sigma2 for a stationary kernel (gptorch/kernels.py:174-179); sum Y^2
+        scal = torch.stack([sigma2.reshape(()) * float(n), nv.logdet_sumsq(None, Y)[1]])
+        if group is not None:
+            torch.distributed.all_reduce(AAf, group=group)
+            torch.distributed.all_reduce(AYf, group=group)
+            torch.distributed.all_reduce(scal, group=group)
+        ctx.kind, ctx.chunk, ctx.group, ctx.n_local = kind, chunk, group, n
+        ctx.save_for_backward(X, Y, Z, ell, sigma2, Lc, dinv, AAf, AYf)
+        return AAf, AYf, scal[0], scal[1]
+
+    @staticmethod
+    def _panel(kind, Xc, Z, ell, sigma2, L, dinv):
+        Kfu = nv.kern_fwd(kind, Xc, Z, ell, sigma2)
+        ld = Kfu.stride(0)
+        nv.call("gpb_trsm_right_lt", nv.ptr(L), L.shape[0], L.stride(0), nv.ptr(dinv), nv.ptr(Kfu), Kfu.shape[0], ld,
+                nv.stream_ptr())
+        return Kfu, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gAA, gAY, g_kd, _g_yy):
+        X, Y, Z, ell, sigma2, L, dinv, AA, AY = ctx.saved_tensors
+        kind, chunk, group = ctx.kind, ctx.chunk, ctx.group
+        n = X.shape[0]
+        S = nv._c(gAA + gAA.t())
+        gAY = nv._c(gAY)
+        T = _tinv(L, dinv)
+        R = nv.gemm(nv.GEMM_NT, S, T)            # S L^-1
+        w = nv.gemm(nv.GEMM_NN, T, gAY)          # L^-T gAY   (m x dy)
+        g_ell = torch.zeros_like(ell.reshape(-1))
+        g_s2 = torch.zeros(1, dtype=torch.float64, device=X.device)
+        gZ = torch.zeros_like(Z)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            At, _ = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, L, dinv)
+            G = nv.gemm(nv.GEMM_NN, At, R)
+            nv.gemm(nv.GEMM_NT, Y[s:e], w, beta=1.0, C=G)
+            ge, gs, gz = nv.kern_bwd(kind, X[s:e], Z, ell, sigma2, G, True)
+            g_ell += ge
+            g_s2 += gs
+            gZ += gz
+        g_s2 += g_kd * float(ctx.n_local)
+        if group is not None:
+            flat = torch.cat([g_ell, g_s2, gZ.reshape(-1)])
+            torch.distributed.all_reduce(flat, group=group)
+            g_ell, g_s2, gZ = flat[: g_ell.numel()], flat[g_ell.numel(): g_ell.numel() + 1], flat[g_ell.numel() + 1:].reshape(Z.shape)
+        Q = nv.gemm(nv.GEMM_NN, S, AA)
+        nv.gemm(nv.GEMM_NT, gAY, AY, beta=1.0, C=Q)
+        gL = nv.gemm(nv.GEMM_NN, T, Q, alpha=-1.0)
+        gL.tril_()
+        return (None, None, None, gZ if ctx.needs_input_grad[3] else None,
+                g_ell.reshape(ell.shape) if ctx.needs_input_grad[4] else None,
+                g_s2.reshape(sigma2.shape) if (sigma2 is not None and ctx.needs_input_grad[5]) else None,
+                gL if ctx.needs_input_grad[6] else None, None, None)

@@ -26,6 +26,8 @@ SIGNATURES = {
     "gpb_version": (c_int, []),
     "gpb_last_error": (ctypes.c_char_p, []),
     "gpb_block_size": (c_int, []),
+    "gpb_launch_count": (c_long, []),
+    "gpb_reset_launch_count": (None, []),
     "gpb_kern_fwd": (c_int, [c_int, c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_int,
                              c_void_p, c_void_p, c_int, c_void_p, c_long, c_void_p]),
     "gpb_kern_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
@@ -37,6 +39,7 @@ SIGNATURES = {
     "gpb_tri_diag_inverse": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p]),
     "gpb_potri_workspace_bytes": (c_size_t, [c_int]),
     "gpb_potri_lower": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpb_trtri_upper": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gpb_potri_assemble": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_long, c_void_p]),
     "gpb_tri_zero_upper": (c_int, [c_void_p, c_int, c_long, c_void_p]),
     "gpb_add_diag": (c_int, [c_void_p, c_int, c_long, c_void_p, c_double, c_void_p]),
@@ -44,7 +47,7 @@ SIGNATURES = {
     "gpb_trsv_lower": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_int, c_long, c_int, c_void_p,
                                c_size_t, c_void_p]),
     "gpb_trsm_right_lt": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_int, c_long, c_void_p]),
-    "gpb_logdet_sumsq": (c_int, [c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_void_p, c_void_p]),
+    "gpb_logdet_sumsq": (c_int, [c_void_p, c_int, c_long, c_void_p, c_int, c_int, c_long, c_void_p, c_void_p]),
     "gpb_gemm": (c_int, [c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double,
                          c_void_p, c_long, c_int, c_void_p]),
     "gpb_gpr_grad_workspace_bytes": (c_size_t, [c_int, c_int]),

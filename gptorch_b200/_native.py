@@ -10,14 +10,68 @@ from ._lib import ptr, stream_ptr, call, query
 
 NB = 128
 
+
+class PhaseTimer:
+    """Optional CUDA-event timing of named phases on the current stream (used by bench.py only).
+
+    ``with phase("potrf"):`` records start/end events when a timer is installed; otherwise it is a no-op.
+    """
+
+    def __init__(self):
+        self.records = []   # (name, start_event, end_event)
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.records:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+_timer = None
+
+
+def install_timer(timer):
+    global _timer
+    _timer = timer
+
+
+class phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _timer is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timer is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _timer.records.append((self.name, self.e0, e1))
+        return False
+
+
+def launch_count():
+    return _lib.load().gpb_launch_count()
+
+
+def reset_launch_count():
+    _lib.load().gpb_reset_launch_count()
+
 KIND = {"Rbf": 0, "SquaredExponential": 0, "Exp": 1, "Matern12": 1, "Matern32": 2, "Matern52": 3, "Linear": 4}
 KERN_LINEAR = 4
 
 
 def _c(t):
-    """Contiguous fp64 CUDA view of t (copies only when needed)."""
+    """fp64 row-major view of t: 1-D/0-D tensors are made contiguous; a 2-D tensor is accepted as is when its
+    rows are dense (stride(1) == 1) even if padded (stride(0) > shape[1]), otherwise it is copied."""
     if t.dtype != torch.float64:
         t = t.to(torch.float64)
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= max(t.shape[1], 1) and t.shape[0] > 1:
+        return t
     return t.contiguous()
 
 
@@ -117,6 +171,14 @@ def potri_(A, lda, dinv):
     return kd
 
 
+def trtri_upper_(A, lda, dinv):
+    """In place: upper triangle of A <- L^-T (diagonal 128-blocks become clean upper-triangular blocks)."""
+    n = A.shape[0]
+    ws_bytes = query("gpb_potri_workspace_bytes", n)
+    ws = _ws(ws_bytes, A.device)
+    call("gpb_trtri_upper", ptr(A), n, lda, ptr(dinv), ptr(ws), ws.numel() * 8, stream_ptr())
+
+
 def potri_assemble(A, lda, kd):
     n = A.shape[0]
     out = torch.empty((n, n), dtype=torch.float64, device=A.device)
@@ -164,13 +226,16 @@ def trsm_right_lt_(L, dinv, X, ldx):
 
 
 def logdet_sumsq(L, V=None):
-    """Returns a 2-element device tensor: [sum log diag L, sum V^2]."""
-    out = torch.empty(2, dtype=torch.float64, device=L.device)
-    n = L.shape[0]
+    """Returns a 2-element device tensor: [sum log diag L (0 if L is None), sum V^2 (0 if V is None)]."""
+    dev = L.device if L is not None else V.device
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    n = L.shape[0] if L is not None else 0
     if V is not None:
-        call("gpb_logdet_sumsq", ptr(L), n, L.stride(0), ptr(V), V.shape[1], V.stride(0), ptr(out), stream_ptr())
+        V = _c(V)
+        call("gpb_logdet_sumsq", ptr(L), n, L.stride(0) if L is not None else 0, ptr(V), V.shape[0], V.shape[1],
+             V.stride(0), ptr(out), stream_ptr())
     else:
-        call("gpb_logdet_sumsq", ptr(L), n, L.stride(0), None, 0, 0, ptr(out), stream_ptr())
+        call("gpb_logdet_sumsq", ptr(L), n, L.stride(0), None, 0, 0, 0, ptr(out), stream_ptr())
     return out
 
 

@@ -12,10 +12,13 @@ size_t potri_workspace_bytes(int n);
 int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream);
 int potri_assemble(const double* A, int n, long lda, const double* kd, double* out, long ldo, cudaStream_t stream);
+int trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace, size_t workspace_bytes,
+                cudaStream_t stream);
 size_t trsv_workspace_bytes(int n);
 int trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, int k, long ldb, int trans,
                void* workspace, size_t workspace_bytes, cudaStream_t stream);
-int logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out, cudaStream_t stream);
+int logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
+                 cudaStream_t stream);
 int tri_zero_upper(double* A, int n, long lda, cudaStream_t stream);
 int add_diag(double* A, int n, long lda, const double* value, double host_value, cudaStream_t stream);
 int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
@@ -43,6 +46,8 @@ extern "C" {
 int gpb_version(void) { return 100; }
 const char* gpb_last_error(void) { return last_error(); }
 int gpb_block_size(void) { return NB; }
+long gpb_launch_count(void) { return launch_count(); }
+void gpb_reset_launch_count(void) { reset_launch_count(); }
 
 int gpb_kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
                  const double* ell, int ell_len, const double* sigma2, const double* noise, int fill, double* K,
@@ -72,6 +77,10 @@ int gpb_potri_lower(double* A, int n, long lda, const double* dinv, double* kdia
                     size_t workspace_bytes, void* stream) {
   return potri_lower(A, n, lda, dinv, kdiag_blocks, workspace, workspace_bytes, S(stream));
 }
+int gpb_trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  return trtri_upper(A, n, lda, dinv, workspace, workspace_bytes, S(stream));
+}
 int gpb_potri_assemble(const double* A, int n, long lda, const double* kdiag_blocks, double* out, long ldo,
                        void* stream) {
   return potri_assemble(A, n, lda, kdiag_blocks, out, ldo, S(stream));
@@ -90,8 +99,9 @@ int gpb_trsm_right_lt(const double* L, int n, long ldl, const double* dinv, doub
                       void* stream) {
   return trsm_right_lt(L, n, ldl, dinv, X, m, ldx, S(stream));
 }
-int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out, void* stream) {
-  return logdet_sumsq(L, n, ldl, V, k, ldv, out, S(stream));
+int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
+                     void* stream) {
+  return logdet_sumsq(L, n, ldl, V, vrows, k, ldv, out, S(stream));
 }
 
 int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,

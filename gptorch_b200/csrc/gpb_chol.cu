@@ -126,6 +126,7 @@ static int launch_diag_block(double* A, long lda, int nb, double* dinv_blk, int*
     attr_set = true;
   }
   diag_block_kernel<<<1, DG_THREADS, DG_SMEM_BYTES, stream>>>(A, lda, nb, dinv_blk, info, j0, do_factor);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }
@@ -328,6 +329,7 @@ int tri_diag_inverse(const double* L, int n, long ldl, double* dinv, cudaStream_
   }
   const int nblk = (n + NB - 1) / NB;
   diag_inverse_batched_kernel<<<nblk, DG_THREADS, DG_SMEM_BYTES, stream>>>(L, ldl, n, dinv);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }
@@ -365,15 +367,18 @@ size_t potri_workspace_bytes(int n) {
   return best * sizeof(double) + 256;
 }
 
-int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
-                size_t workspace_bytes, cudaStream_t stream) {
+// T = L^-T into the upper triangle of A (diagonal 128-blocks are overwritten by T_jj with zeros below the
+// diagonal; the strictly-lower off-diagonal blocks keep L).
+int trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace, size_t workspace_bytes,
+                cudaStream_t stream) {
   if (n <= 0) return GPB_OK;
-  if (!A || !dinv || !kdiag_blocks || lda < n) return GPB_ERR_BADARG;
+  if (!A || !dinv || lda < n) return GPB_ERR_BADARG;
   if (workspace_bytes < potri_workspace_bytes(n) || (n > NB && !workspace)) return GPB_ERR_BADARG;
   const int nblk = (n + NB - 1) / NB;
   {
     dim3 grid(NB / 32, NB / 32, nblk);
     tinv_base_kernel<<<grid, 256, 0, stream>>>(A, lda, n, dinv);
+    count_launch();
     GPB_CUDA_CHECK(cudaGetLastError());
   }
   CUtensorMap mapA128, mapA16;
@@ -426,6 +431,18 @@ int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_bl
       if (rc) return rc;
     }
   }
+  return GPB_OK;
+}
+
+int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream) {
+  if (n <= 0) return GPB_OK;
+  if (!kdiag_blocks) return GPB_ERR_BADARG;
+  int rc = trtri_upper(A, n, lda, dinv, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  CUtensorMap mapA128;
+  rc = make_tmap_f64(&mapA128, A, n, n, lda, 128);
+  if (rc) return rc;
   // Kinv = T T^T: strictly-lower blocks in place, diagonal blocks to kdiag_blocks.
   GemmArgs g;
   g.M = n; g.N = n; g.K = n;
@@ -467,6 +484,7 @@ int potri_assemble(const double* A, int n, long lda, const double* kd, double* o
   const int nt = (n + 31) / 32;
   dim3 grid(nt, nt);
   potri_assemble_kernel<<<grid, 256, 0, stream>>>(A, lda, n, kd, out, ldo);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }

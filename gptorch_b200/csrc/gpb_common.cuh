@@ -24,6 +24,10 @@
 namespace gpb {
 
 void set_last_error(cudaError_t e, const char* file, int line);
+// Every kernel launch of this library is counted (bench.py reports it as gpu_launches).
+void count_launch(int n = 1);
+long launch_count();
+void reset_launch_count();
 
 // Block size every blocked algorithm in this library is built on (diagonal blocks, Dinv workspace).
 constexpr int NB = 128;

@@ -246,6 +246,7 @@ static int launch_mode(const CUtensorMap& mapA, const CUtensorMap& mapB, const G
   }
   dim3 grid(ntiles, batch, 1);
   gemm_dmma_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(mapA, mapB, kp);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }

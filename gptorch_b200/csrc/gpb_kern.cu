@@ -188,6 +188,9 @@ __global__ void __launch_bounds__(KF_THREADS, 1) kern_fwd_kernel(const KfwdParam
         } else {
           double r2 = (nrow + nbv[lc + e]) - 2.0 * dot;  // gptorch/util.py:84
           r2 = fmax(r2, 0.0);                             // value of r2 - clamp(r2, max=0) (gptorch/util.py:88)
+          // K(X) diagonal: the reference's expansion leaves O(1e-16) round-off here, which sqrt() turns into
+          // O(1e-8) noise for Exp/Matern; the distance of a point to itself is exactly 0.
+          if (p.symmetric && row == col + e) r2 = 0.0;
           v[e] = sig2 * kern_base(p.kind, r2);
         }
         if (p.symmetric && row == col + e) v[e] += noise;
@@ -226,6 +229,7 @@ int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int 
   p.tiles_n = (p.n2 + KF_TILE - 1) / KF_TILE;
   const int ntiles = p.lower ? tiles_m * (tiles_m + 1) / 2 : tiles_m * p.tiles_n;
   kern_fwd_kernel<<<ntiles, KF_THREADS, 0, stream>>>(p);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }
@@ -249,6 +253,7 @@ int linear_kdiag(const double* X, int n, long ldx, int D, const double* v, doubl
   if (n <= 0) return GPB_OK;
   if (!X || !v || !out || D <= 0) return GPB_ERR_BADARG;
   linear_kdiag_kernel<<<(n + 255) / 256, 256, 0, stream>>>(X, n, ldx, D, v, out);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }
@@ -533,12 +538,14 @@ static int kbwd_launch(KbwdParams& p, int ncb, double* g_ell, double* g_sigma2, 
   }
   dim3 grid(ncb, p.strips);
   kern_bwd_kernel<GPR><<<grid, KB_THREADS, smem, stream>>>(p);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   const int ncta = ncb * p.strips;
   const long work = std::max<long>(p.D + 2, gX2 ? static_cast<long>(p.n2) * p.D : 0);
   const int blocks = static_cast<int>(std::min<long>((work + 255) / 256, 1024));
   kbwd_finalize_kernel<<<blocks, 256, 0, stream>>>(p.kind, p.D, p.ell_len, p.ell, ncta, p.part_h, p.strips, p.n2,
                                                    gX2 ? p.part_g2 : nullptr, g_ell, g_sigma2, g_noise, gX2);
+                                                   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }

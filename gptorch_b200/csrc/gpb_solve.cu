@@ -210,6 +210,7 @@ int trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, 
       else if (kr == 2) trsv_bwd_kernel<2><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
       else trsv_bwd_kernel<4><<<nblk, TRSV_THREADS, 0, stream>>>(L, ldl, n, dinv, B, ldb, col0, kr, flags, ticket);
     }
+    count_launch();
     GPB_CUDA_CHECK(cudaGetLastError());
   }
   return GPB_OK;
@@ -219,7 +220,7 @@ int trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, 
 // out[0] = sum log L_ii ; out[1] = sum V^2.  One CTA, fixed reduction tree => deterministic.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) logdet_sumsq_kernel(const double* __restrict__ L, int n, long ldl,
-                                                            const double* __restrict__ V, int k, long ldv,
+                                                            const double* __restrict__ V, int vrows, int k, long ldv,
                                                             double* __restrict__ out) {
   __shared__ double scratch[32];
   double s = 0.0;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(1024) logdet_sumsq_kernel(const double* __rest
   if (threadIdx.x == 0) out[0] = s;
   double q = 0.0;
   if (V != nullptr) {
-    const long total = static_cast<long>(n) * k;
+    const long total = static_cast<long>(vrows) * k;
     for (long idx = threadIdx.x; idx < total; idx += blockDim.x) {
       const long r = idx / k, c = idx - r * k;
       const double v = V[r * ldv + c];
@@ -239,10 +240,11 @@ __global__ void __launch_bounds__(1024) logdet_sumsq_kernel(const double* __rest
   if (threadIdx.x == 0) out[1] = q;
 }
 
-int logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out,
+int logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
                  cudaStream_t stream) {
-  if (!L || !out || n < 0) return GPB_ERR_BADARG;
-  logdet_sumsq_kernel<<<1, 1024, 0, stream>>>(L, n, ldl, V, k, ldv, out);
+  if (!out || n < 0 || (n > 0 && !L)) return GPB_ERR_BADARG;
+  logdet_sumsq_kernel<<<1, 1024, 0, stream>>>(L, n, ldl, V, vrows, k, ldv, out);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }
@@ -258,6 +260,7 @@ int tri_zero_upper(double* A, int n, long lda, cudaStream_t stream) {
   if (!A || lda < n) return GPB_ERR_BADARG;
   dim3 grid((n + 255) / 256, n);
   tri_zero_upper_kernel<<<grid, 256, 0, stream>>>(A, n, lda);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }
@@ -272,6 +275,7 @@ int add_diag(double* A, int n, long lda, const double* value, double host_value,
   if (n <= 0) return GPB_OK;
   if (!A || lda < n) return GPB_ERR_BADARG;
   add_diag_kernel<<<(n + 255) / 256, 256, 0, stream>>>(A, n, lda, value, host_value);
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }

@@ -2,6 +2,7 @@
 #include "gpb_common.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -15,6 +16,11 @@ void set_last_error(cudaError_t e, const char* file, int line) {
 }
 void set_last_error_msg(const char* msg) { snprintf(g_last_error, sizeof(g_last_error), "%s", msg); }
 const char* last_error() { return g_last_error; }
+
+static std::atomic<long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void reset_launch_count() { g_launches.store(0, std::memory_order_relaxed); }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;

@@ -1,0 +1,203 @@
+"""GPModel: data + kernel + likelihood + mean function, prediction wrappers and optimisers
+(reference: gptorch/models/base.py)."""
+from time import time
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+
+from .. import likelihoods, settings
+from ..functions import cholesky
+from ..mean_functions import Zero
+from ..model import Model
+from ..util import TensorType, as_tensor, torch_dtype
+
+
+def input_as_tensor(predict_func):
+    """Decorator for the public predict_* methods: accept numpy or tensors on any device, run on the model's
+    device, hand the result back in the caller's format (gptorch/models/base.py:21-55)."""
+
+    def convert(out, fn):
+        if isinstance(out, torch.Tensor):
+            return fn(out)
+        if isinstance(out, tuple):
+            return tuple(fn(o) for o in out)
+        raise NotImplementedError("Unhandled output type {}".format(type(out)))
+
+    def predict(obj, input_new, *args, **kwargs):
+        from_numpy = isinstance(input_new, np.ndarray)
+        if from_numpy:
+            x = torch.as_tensor(input_new, dtype=torch_dtype).to(obj.Y.device)
+        else:
+            caller_device = input_new.device
+            x = input_new.to(obj.Y.device)
+        out = predict_func(obj, x, *args, **kwargs)
+        if from_numpy:
+            return convert(out, lambda o: o.detach().cpu().numpy())
+        return convert(out, lambda o: o.to(caller_device))
+
+    return predict
+
+
+_SCIPY_METHODS = ("CG", "BFGS", "Newton-CG", "Nelder-Mead", "Powell", "L-BFGS-B", "TNC", "COBYLA", "SLSQP",
+                  "dogleg", "trust-ncg")
+
+_DEFAULT_LR = {"SGD": 0.001, "Adam": 0.01, "LBFGS": 1.0, "Adadelta": 1.0, "Adagrad": 0.01, "Adamax": 0.002,
+               "ASGD": 0.01, "RMSprop": 0.01, "Rprop": 0.01}
+
+
+def _make_torch_optimizer(method, params, lr):
+    """The reference's optimiser table (gptorch/models/base.py:131-207)."""
+    o = torch.optim
+    if method == "SGD":
+        return o.SGD(params, lr=lr, momentum=0.9)
+    if method == "Adam":
+        return o.Adam(params, lr=lr)
+    if method == "LBFGS":
+        return o.LBFGS(params, lr=lr, max_iter=5, max_eval=None, tolerance_grad=1e-05, tolerance_change=1e-09,
+                       history_size=50, line_search_fn=None)
+    if method == "Adadelta":
+        return o.Adadelta(params, lr=lr, rho=0.9, eps=1e-06, weight_decay=0.00001)
+    if method == "Adagrad":
+        return o.Adagrad(params, lr=lr, lr_decay=0, weight_decay=0)
+    if method == "Adamax":
+        return o.Adamax(params, lr=lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=0)
+    if method == "ASGD":
+        return o.ASGD(params, lr=lr, lambd=0.0001, alpha=0.75, t0=1000000.0, weight_decay=0)
+    if method == "RMSprop":
+        return o.RMSprop(params, lr=lr, alpha=0.99, eps=1e-08, weight_decay=0.00, momentum=0.01, centered=False)
+    if method == "Rprop":
+        return o.Rprop(params, lr=lr, etas=(0.5, 1.2), step_sizes=(1e-06, 50))
+    return None
+
+
+class GPModel(Model):
+    """Base class of the GP models."""
+
+    def __init__(self, x, y, kernel, likelihood, mean_function, name="gp"):
+        super().__init__()
+        self.kernel = kernel
+        self.likelihood = likelihood if likelihood is not None else GPModel._init_gaussian_likelihood(y)
+        self.mean_function = mean_function if mean_function is not None else Zero(y.shape[1])
+        x, y = as_tensor(x), as_tensor(y)
+        x.requires_grad_(False)
+        y.requires_grad_(False)
+        self.X, self.Y = x, y   # plain attributes (not buffers), as in the reference
+        self.__class__.__name__ = name
+
+    @property
+    def num_data(self):
+        return self.Y.shape[0]
+
+    @property
+    def input_dimension(self):
+        return self.X.shape[1]
+
+    @property
+    def output_dimension(self):
+        return self.Y.shape[1]
+
+    @staticmethod
+    def _init_gaussian_likelihood(y):
+        """Noise std of roughly 3% of the output spread (gptorch/models/base.py:101-109)."""
+        return likelihoods.Gaussian(variance=0.001 * float(y.var()))
+
+    # ---- training -----------------------------------------------------------------------------------
+    def optimize(self, method="Adam", max_iter=2000, verbose=True, learning_rate=None):
+        """Minimise loss() over the trainable parameters with a torch optimiser or scipy.optimize.minimize
+        (gptorch/models/base.py:111-296).  Returns (losses, seconds) for torch optimisers, the scipy result
+        otherwise."""
+        if method in _SCIPY_METHODS:
+            print("Scipy.optimize.minimize...")
+            return self._optimize_scipy(method=method, maxiter=max_iter, disp=verbose)
+        lr = learning_rate if learning_rate is not None else _DEFAULT_LR.get(method)
+        if method == "SGD" and learning_rate is None:
+            lr = 0.01  # GPs take a more aggressive step than the usual NN default
+        params = [p for p in self.parameters() if p.requires_grad]
+        self.optimizer = _make_torch_optimizer(method, params, lr)
+        if self.optimizer is None:
+            raise ValueError(
+                "Optimizer %s is not found. Please choose one of the following optimizers supported in PyTorch: "
+                "Adadelt, Adagrad, Adam, Adamax, ASGD, LBFGS, RMSprop, Rprop, SGD. Or the optimizers supported by "
+                "scipy.optimize.minimize: BFGS, L-BFGS-B, CG, Newton-CG, Nelder-Mead, Powell, TNC, COBYLA, SLSQP, "
+                "dogleg, trust-ncg, etc." % method)
+
+        def closure():
+            self.optimizer.zero_grad()
+            value = self.loss()
+            value.backward()
+            return value
+
+        losses = np.zeros(max_iter)
+        tic = time()
+        print("{}: Start optimizing via {}".format(self.__class__.__name__, method))
+        report_every = 1 if verbose else 20
+        for idx in range(max_iter):
+            if method == "LBFGS":
+                value = self.optimizer.step(closure)
+                if isinstance(value, float):  # converged
+                    losses[idx] = value
+                    losses = losses[: idx + 1]
+                    break
+            else:
+                value = closure()
+                self.optimizer.step()
+            losses[idx] = value.item()
+            if idx % report_every == 0:
+                print("Iter: %d\tLoss: %s" % (idx, losses[idx]))
+        t = time() - tic
+        print("Optimization time taken: %s s" % t)
+        print("Optimization method: %s" % str(self.optimizer))
+        if len(losses) == max_iter:
+            print("Optimization terminated by reaching the maximum iterations")
+        else:
+            print("Optimization terminated by getting below the tolerant error")
+        return losses, t
+
+    def _optimize_scipy(self, method="L-BFGS-B", tol=None, callback=None, maxiter=1000, disp=True):
+        return minimize(fun=self._loss_and_grad, x0=self._get_param_array(), method=method, jac=True, tol=tol,
+                        callback=callback, options=dict(disp=disp, maxiter=maxiter))
+
+    # ---- prediction -----------------------------------------------------------------------------------
+    def _predict(self, input_new, diag=True):
+        """(mean [n, dy], variance [n, dy]) if diag else (mean, covariance [n, n])."""
+        raise NotImplementedError()
+
+    @input_as_tensor
+    def predict_f(self, input_new, diag=True, **kwargs):
+        return self._predict(input_new, diag=diag, **kwargs)
+
+    @input_as_tensor
+    def predict_y(self, input_new, diag=True, **kwargs):
+        mean_f, cov_f = self._predict(input_new, diag=diag, **kwargs)
+        if diag:
+            return self.likelihood.predict_mean_variance(mean_f, cov_f)
+        return self.likelihood.predict_mean_covariance(mean_f, cov_f)
+
+    def _sample(self, mu, sigma, n_samples):
+        root = cholesky(sigma)
+        noise = torch.randn(n_samples, *mu.shape, dtype=torch_dtype, device=root.device)
+        return mu + root[None, :, :] @ noise
+
+    @input_as_tensor
+    def predict_f_samples(self, input_new, n_samples=1, **kwargs):
+        """[n_samples, n_test, dy] draws from p(f* | y) (gptorch/models/base.py:362-375)."""
+        mu, sigma = self.predict_f(input_new, diag=False, **kwargs)
+        return self._sample(mu, sigma, n_samples)
+
+    @input_as_tensor
+    def predict_y_samples(self, input_new, n_samples=1, **kwargs):
+        mu, sigma = self.predict_y(input_new, diag=False, **kwargs)
+        return self._sample(mu, sigma, n_samples)
+
+    # ---- device moves: the data are attributes, not buffers ---------------------------------------------
+    def cuda(self):
+        super().cuda()
+        self.X, self.Y = self.X.cuda(), self.Y.cuda()
+
+    def cpu(self):
+        super().cpu()
+        self.X, self.Y = self.X.cpu(), self.Y.cpu()
+
+    def _loss(self, *args, **kwargs):
+        return -(self.log_likelihood(*args, **kwargs) + self.log_prior())

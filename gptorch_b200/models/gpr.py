@@ -1,0 +1,72 @@
+"""Exact GP regression (reference: gptorch/models/gpr.py)."""
+import torch
+
+from .. import _autograd as ag
+from .. import _native as nv
+from .. import kernels
+from ..functions import cholesky, trtrs, mm, mm_nt
+from ..likelihoods import Gaussian
+from .base import GPModel
+
+
+def _native_kind(kernel):
+    """Index of the fused native kernel family, or None when the kernel has to be composed in torch."""
+    if isinstance(kernel, kernels.Stationary) and kernel._kind is not None and type(kernel).K is kernels.Stationary.K:
+        return kernel._kind
+    return None
+
+
+class GPR(GPModel):
+    """Gaussian-process regression with a Gaussian likelihood."""
+
+    def __init__(self, x, y, kernel, mean_function=None, likelihood=None, name="gpr"):
+        super().__init__(x, y, kernel, likelihood, mean_function, name)
+
+    def log_likelihood(self, x=None, y=None):
+        """log p(y | x, theta), shape [1] (Rasmussen & Williams alg. 2.1; gptorch/models/gpr.py:47-67).
+
+        With a stationary kernel and the Gaussian likelihood the whole evaluation is one fused native node
+        (covariance build -> Cholesky -> solve -> log-det, analytic backward).  Other kernels (Sum, Product,
+        Linear, ...) go through the reference's step-by-step form on the native primitives.
+        """
+        x = x if x is not None else self.X
+        y = y if y is not None else self.Y
+        if x.shape[0] != y.shape[0]:
+            raise ValueError("X and Y must have same # data.")
+        n, dy = y.shape
+        resid = y - self.mean_function(x)
+        kind = _native_kind(self.kernel)
+        if kind is not None and isinstance(self.likelihood, Gaussian):
+            return ag.GPRLogLikFn.apply(kind, x, resid, self.kernel.length_scales.transform(),
+                                        self.kernel.variance.transform(), self.likelihood.variance.transform())
+        L = cholesky(self._compute_kyy(x=x))
+        alpha = trtrs(resid, L)
+        red_logdet = ag.LogDetFn.apply(L)
+        const = -0.5 * dy * n * torch.log(torch.tensor(2.0 * torch.pi, dtype=alpha.dtype, device=alpha.device))
+        return (-0.5 * alpha.pow(2).sum() - dy * red_logdet + const).reshape(1)
+
+    def _compute_kyy(self, x=None):
+        """K(x, x) + noise * I (gptorch/models/gpr.py:69-86)."""
+        x = x if x is not None else self.X
+        kind = _native_kind(self.kernel)
+        noise = self.likelihood.variance.transform()
+        if kind is not None:
+            return ag.KernelFn.apply(kind, x.to(torch.float64), None, self.kernel.length_scales.transform(),
+                                     self.kernel.variance.transform(), noise)
+        n = x.shape[0]
+        return self.kernel.K(x) + noise * torch.eye(n, dtype=x.dtype, device=x.device)
+
+    def _predict(self, x_new, diag=True, x=None):
+        """p(f* | y): mean [n*, dy] and variance [n*, dy] (diag) or covariance [n*, n*]
+        (gptorch/models/gpr.py:88-117)."""
+        x = x if x is not None else self.X
+        k_sy = self.kernel.K(x_new, x)                       # [n*, n]
+        L = cholesky(self._compute_kyy(x=x))
+        At = trtrs(k_sy.t(), L).t()                          # (L^-1 k_ys)^T, solved on the row panel k_sy L^-T
+        V = trtrs(self.Y - self.mean_function(x), L)
+        mean_f = mm(At, V) + self.mean_function(x_new)
+        if diag:
+            var_f = (self.kernel.Kdiag(x_new) - (At * At).sum(1))[:, None].expand_as(mean_f)
+        else:
+            var_f = self.kernel.K(x_new) - mm_nt(At, At)
+        return mean_f, var_f

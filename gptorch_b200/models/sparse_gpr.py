@@ -1,0 +1,211 @@
+"""Sparse GPs with inducing points: VFE (Titsias 2009) and SVGP (Hensman et al. 2013/2015)
+(reference: gptorch/models/sparse_gpr.py).
+
+Both models work on ROW panels Kfu = K(x, Z) [n, M] (the transpose of the reference's Kuf) so that every
+O(n M^2) step is an NT / TN product on the native DMMA engine: A^T = Kfu L^-T, A A^T = (A^T)^T A^T, ...
+VFE never materialises Kuf: it streams row chunks of x through `VfeStatsFn`, which is also the point where an
+N-sharded multi-GPU run all-reduces its M x M statistics.
+"""
+import numpy as np
+import torch
+from torch.distributions.transforms import LowerCholeskyTransform
+
+from .. import _autograd as ag
+from .. import settings
+from ..functions import cholesky, trtrs, mm, mm_nt, mm_tn
+from ..likelihoods import Gaussian
+from ..mean_functions import Zero
+from ..model import Param
+from ..util import as_tensor, kmeans_centers, torch_dtype
+from .base import GPModel
+from .gpr import GPR, _native_kind
+
+VFE_CHUNK_ROWS = 1 << 17   # rows of x per streamed panel (128Ki x M fp64: 1 GiB at M = 1024)
+
+
+class _InducingPointsGP(GPModel):
+    """Common part of the inducing-point models: Z is a trainable, un-transformed Param
+    (gptorch/models/sparse_gpr.py:24-73)."""
+
+    def __init__(self, x, y, kernel, num_inducing_points=None, inducing_points=None, mean_function=None,
+                 likelihood=None):
+        super().__init__(x, y, kernel, likelihood, mean_function)
+        if inducing_points is None:
+            if num_inducing_points is None:
+                num_inducing_points = np.clip(x.shape[0] // 10, 1, 100)
+            x_host = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
+            inducing_points = kmeans_centers(x_host, num_inducing_points, perturb_if_fail=True)
+        self.Z = Param(as_tensor(inducing_points))
+        self._group = None          # torch.distributed process group when the rows of X are sharded
+        self._num_data_global = None
+
+    @property
+    def num_inducing(self):
+        return self.Z.shape[0]
+
+    def distribute(self, group=None):
+        """Declare that self.X / self.Y hold this rank's shard of the rows.  Must be called on
+        every rank after torch.distributed.init_process_group."""
+        import torch.distributed as dist
+        self._group = group if group is not None else dist.group.WORLD
+        n = torch.tensor([float(self.Y.shape[0])], dtype=torch_dtype, device=self.Y.device)
+        dist.all_reduce(n, group=self._group)
+        self._num_data_global = int(n.item())
+        return self
+
+    @property
+    def num_data(self):
+        return self._num_data_global if self._num_data_global is not None else self.Y.shape[0]
+
+
+class FITC(_InducingPointsGP):
+    """Placeholder, as in the reference (gptorch/models/sparse_gpr.py:76-90)."""
+    pass
+
+
+class VFE(_InducingPointsGP):
+    """Variational free energy (collapsed bound) sparse GP regression."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert isinstance(self.mean_function, Zero), "Mean functions not implemented for VFE yet."
+
+    def _stats(self, x, L):
+        """(A A^T, A Y, sum Kdiag, sum Y^2) with A = L^-1 Kuf and Y = self.Y (the reference ignores the y
+        argument of log_likelihood, gptorch/models/sparse_gpr.py:125)."""
+        kind = _native_kind(self.kernel)
+        if kind is not None:
+            return ag.VfeStatsFn.apply(kind, x, self.Y, self.Z, self.kernel.length_scales.transform(),
+                                       self.kernel.variance.transform(), L, VFE_CHUNK_ROWS, self._group)
+        if self._group is not None:
+            raise NotImplementedError("row-sharded VFE needs a stationary kernel")
+        At = ag.TrsmRightFn.apply(self.kernel.K(x, self.Z), L, ag._dinv_of(L))
+        return mm_tn(At, At), mm_tn(At, self.Y), self.kernel.Kdiag(x).sum(), self.Y.pow(2).sum()
+
+    def _core(self, x):
+        noise = self.likelihood.variance.transform()
+        m = self.num_inducing
+        L = cholesky(self.kernel.K(self.Z))
+        AA, AY, kd_sum, yy = self._stats(x, L)
+        AAT = AA / noise
+        B = AAT + torch.eye(m, dtype=torch_dtype, device=AAT.device)
+        LB = cholesky(B)
+        c = trtrs(AY, LB) / noise
+        return noise, L, AAT, LB, c, kd_sum, yy
+
+    def log_likelihood(self, x=None, y=None):
+        """Titsias' bound, eq. (9); 0-dim tensor (gptorch/models/sparse_gpr.py:108-153)."""
+        x = x if x is not None else self.X
+        y = y if y is not None else self.Y
+        if x.shape[0] != y.shape[0]:
+            raise ValueError("X and Y must have same # data.")
+        n = self.num_data if self._group is not None else x.shape[0]
+        dy = self.output_dimension
+        noise, L, AAT, LB, c, kd_sum, yy = self._core(x)
+        elbo = -0.5 * dy * n * np.log(2 * np.pi)
+        elbo = elbo - dy * ag.LogDetFn.apply(LB)
+        elbo = elbo - 0.5 * dy * n * noise.log()
+        elbo = elbo - 0.5 * (yy + dy * kd_sum) / noise
+        elbo = elbo + 0.5 * c.pow(2).sum()
+        elbo = elbo + 0.5 * dy * AAT.diagonal().sum()
+        return elbo[0]
+
+    def _predict(self, x_new, diag=True, x=None):
+        """p(f* | y) with the inducing outputs integrated out (gptorch/models/sparse_gpr.py:155-195).
+        Unlike the reference this does not freeze Z as a side effect."""
+        x = x if x is not None else self.X
+        noise, L, AAT, LB, c, _, _ = self._core(x)
+        T1 = ag.TrsmRightFn.apply(self.kernel.K(x_new, self.Z), L, ag._dinv_of(L))     # (L^-1 Kus)^T
+        T2 = ag.TrsmRightFn.apply(T1, LB, ag._dinv_of(LB))                             # (LB^-1 L^-1 Kus)^T
+        mean = mm(T2, c)
+        if diag:
+            var = (self.kernel.Kdiag(x_new) - T1.pow(2).sum(1) + T2.pow(2).sum(1))[:, None].expand_as(mean)
+        else:
+            var = self.kernel.K(x_new) + mm_nt(T2, T2) - mm_nt(T1, T1)
+        return mean, var
+
+
+def minibatch(loss_func):
+    """Draw a random subset of the data when none is given (gptorch/models/sparse_gpr.py:198-216)."""
+
+    def wrapped(obj, x=None, y=None):
+        if x is not None:
+            assert y is not None
+        elif obj.batch_size is not None:
+            i = np.random.permutation(obj.Y.shape[0])[: obj.batch_size]
+            i = torch.as_tensor(i, device=obj.X.device)
+            x, y = obj.X[i, :], obj.Y[i, :]
+        else:
+            x, y = obj.X, obj.Y
+        return loss_func(obj, x, y)
+
+    return wrapped
+
+
+class SVGP(_InducingPointsGP):
+    """Sparse variational GP with an explicit Gaussian q(u) = N(induced_output_mean + m(Z), L_S L_S^T)."""
+
+    def __init__(self, y, x, kernel, num_inducing_points=None, inducing_points=None, mean_function=None,
+                 likelihood=None, batch_size=None):
+        # NB the first two positional arguments are (inputs, outputs) despite their names -- the reference
+        # swaps the names but passes them through positionally (gptorch/models/sparse_gpr.py:230-253).
+        if likelihood is None:
+            likelihood = Gaussian()
+        super().__init__(y, x, kernel, num_inducing_points=num_inducing_points, inducing_points=inducing_points,
+                         mean_function=mean_function, likelihood=likelihood)
+        self.batch_size = batch_size
+        self.induced_output_mean, self.induced_output_chol_cov = self._init_posterior()
+
+    def _whitened(self, chol_kuu):
+        """beta = L^-1 L_S and t = L^-1 m_u, shared by the bound and the prediction."""
+        L_S = self.induced_output_chol_cov.transform()
+        return trtrs(L_S, chol_kuu), trtrs(self.induced_output_mean, chol_kuu), L_S
+
+    @minibatch
+    def log_likelihood(self, x, y):
+        """Variational bound on a (mini)batch; 0-dim tensor (gptorch/models/sparse_gpr.py:263-308)."""
+        if x.shape[0] != y.shape[0]:
+            raise ValueError("X and Y must have same # data.")
+        chol_kuu = cholesky(self.kernel.K(self.Z))
+        beta, t, L_S = self._whitened(chol_kuu)
+        f_mean, f_var = self._predict(x, diag=True, chol_kuu=chol_kuu, _whitened=(beta, t))
+        mll = torch.stack([self.likelihood.expected_log_density(m_i, v_i, y_i)
+                           for m_i, v_i, y_i in zip(f_mean.t(), f_var.t(), y.t())]).sum()
+        batch = x.shape[0]
+        world = 1
+        if self._group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self._group)
+            batch = batch * world           # every rank draws the same batch size from its shard
+        mll = mll * (self.num_data / batch)
+        # KL(q(u) || p(u)), summed over output dimensions (the mean function shifts both and cancels):
+        m, dy = self.num_inducing, self.output_dimension
+        kl = 0.5 * dy * (beta.pow(2).sum() - m + 2.0 * ag.LogDetFn.apply(chol_kuu) - 2.0 * L_S.diagonal().log().sum())
+        kl = kl + 0.5 * t.pow(2).sum()
+        return mll - kl / world             # summed over ranks this is the global bound
+
+    def _init_posterior(self):
+        """Initial q(u) from an exact GP on at most 100 random points (gptorch/models/sparse_gpr.py:310-335)."""
+        i = np.random.permutation(self.Y.shape[0])[0: min(self.Y.shape[0], 100)]
+        idx = torch.as_tensor(i, device=self.X.device)
+        x, y = self.X[idx], self.Y[idx]
+        likelihood = self.likelihood if isinstance(self.likelihood, Gaussian) else Gaussian(variance=0.01 * float(y.var()))
+        model = GPR(x, y, self.kernel, mean_function=self.mean_function, likelihood=likelihood)
+        with torch.no_grad():
+            mean, cov = model._predict(self.Z.detach(), diag=False)
+            mean = mean - self.mean_function(self.Z)
+            chol_cov = cholesky(cov)
+        return Param(mean.contiguous()), Param(chol_cov.contiguous(), transform=LowerCholeskyTransform())
+
+    def _predict(self, x_new, diag=True, chol_kuu=None, _whitened=None, **kwargs):
+        """q(f*) mean [n, dy] and variance [n, dy] / covariance [n, n] (gptorch/models/sparse_gpr.py:337-381)."""
+        chol_kuu = cholesky(self.kernel.K(self.Z)) if chol_kuu is None else chol_kuu
+        beta, t = _whitened if _whitened is not None else self._whitened(chol_kuu)[:2]
+        alpha = ag.TrsmRightFn.apply(self.kernel.K(x_new, self.Z), chol_kuu, ag._dinv_of(chol_kuu))   # [n, M]
+        f_mean = mm(alpha, t) + self.mean_function(x_new)
+        gamma = mm(alpha, beta)
+        if diag:
+            f_cov = (self.kernel.Kdiag(x_new) - torch.sum(alpha ** 2, dim=1) + torch.sum(gamma ** 2, dim=1))[:, None].expand_as(f_mean)
+        else:
+            f_cov = self.kernel.K(x_new) - mm_nt(alpha, alpha) + mm_nt(gamma, gamma)
+        return f_mean, f_cov

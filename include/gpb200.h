@@ -49,6 +49,9 @@ int gpb_version(void);
 const char* gpb_last_error(void);
 /* ABI block size: diagonal-block workspaces (`dinv`, `kdiag_blocks`) are ceil(n/128)*128 rows of 128 doubles. */
 int gpb_block_size(void);
+/* Number of CUDA kernels this library has launched since load / the last reset (bench.py: gpu_launches). */
+long gpb_launch_count(void);
+void gpb_reset_launch_count(void);
 
 /* ---- covariance construction ---------------------------------------------------------------------------
  * K[i][j] = k(X[i,:], X2[j,:]).  Replaces Kernel.K(X, X2) (gptorch/kernels.py:189,198,205,220,258) with its
@@ -105,6 +108,12 @@ size_t gpb_potri_workspace_bytes(int n);
  * in kdiag_blocks (ceil(n/128)*128 x 128, symmetric, full); the upper triangle of A is scratch. */
 int gpb_potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* First half of gpb_potri_lower on its own: T = L^-T is written to the UPPER triangle of A (diagonal 128-blocks
+ * become T_jj with zeros below the diagonal; strictly-lower off-diagonal blocks keep L).  Used for the
+ * backward of functions.cholesky / trtrs (dL/dA = L^-T Phi(L^T dL) L^-1 becomes three GEMMs with T).
+ * Workspace size: gpb_potri_workspace_bytes(n). */
+int gpb_trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace, size_t workspace_bytes,
+                    void* stream);
 /* Expand the blocked result of gpb_potri_lower into a full symmetric n x n matrix `out` (ldo). */
 int gpb_potri_assemble(const double* A, int n, long lda, const double* kdiag_blocks, double* out, long ldo,
                        void* stream);
@@ -127,10 +136,10 @@ int gpb_trsv_lower(const double* L, int n, long ldl, const double* dinv, double*
 int gpb_trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* X, int m, long ldx,
                       void* stream);
 
-/* out[0] = sum_i log L[i][i]  (functions.lt_log_determinant, gptorch/functions.py:61-68);
- * out[1] = sum of squares of the n x k matrix V (ldv) if V != NULL (the -1/2 sum alpha^2 term,
- * gptorch/models/gpr.py:66).  Deterministic (fixed reduction order). */
-int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int k, long ldv, double* out,
+/* out[0] = sum_i log L[i][i], i < n  (functions.lt_log_determinant, gptorch/functions.py:61-68; n = 0 skips it);
+ * out[1] = sum of squares of the vrows x k matrix V (ldv) if V != NULL (the -1/2 sum alpha^2 term of
+ * gptorch/models/gpr.py:66, and sum Y^2 of gptorch/models/sparse_gpr.py:146).  Deterministic (fixed order). */
+int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
                      void* stream);
 
 /* ---- GEMM ------------------------------------------------------------------------------------------------
