@@ -1,0 +1,143 @@
+"""The oracle against the reference's own fixtures and against vectors produced by running the reference
+(tests/golden/*.npz, written by oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Cases, case_inputs, rel_err
+from oracle import gp_oracle as O
+
+T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+_GPR = Cases("gpr_cases.npz")
+_VFE = Cases("vfe_cases.npz")
+_SVGP = Cases("svgp_cases.npz")
+
+
+@pytest.mark.parametrize("name", ["Rbf", "Exp", "Matern12", "Matern32", "Matern52"])
+def test_stationary_kernels_match_reference_goldens(fixtures, name):
+    """test/test_kernels.py:59-127: K(x1), K(x1,x2), K(x2,x1)^T, Kdiag, shift invariance, ARD."""
+    x1, x2 = T(fixtures.raw("kern/x1")), T(fixtures.raw("kern/x2"))
+    one = torch.ones(1, dtype=torch.float64)
+    ard = T(fixtures.raw("kern/ard_length_scales"))
+    kx = O.cov(name, x1, None, one, one).numpy()
+    assert np.allclose(kx, fixtures.raw("kern/%s_kx" % name))
+    assert np.allclose(kx, kx.T)
+    assert np.allclose(O.cov(name, x1, x2, one, one).numpy(), fixtures.raw("kern/%s_kx2" % name))
+    assert np.allclose(O.cov(name, x2, x1, one, one).numpy().T, fixtures.raw("kern/%s_kx2" % name))
+    assert np.allclose(O.cov_diag(name, x1, one).numpy(), fixtures.raw("kern/%s_kdiag" % name))
+    assert np.allclose(O.cov(name, x1 + 0.34, None, one, one).numpy(), fixtures.raw("kern/%s_kx" % name))
+    assert np.allclose(O.cov(name, x1, None, ard, one).numpy(), fixtures.raw("kern/%s_kx_ard" % name))
+    assert np.allclose(O.cov(name, x1, x2, ard, one).numpy(), fixtures.raw("kern/%s_kx2_ard" % name))
+    assert np.allclose(O.cov_diag(name, x1, one).numpy(), fixtures.raw("kern/%s_kdiag_ard" % name))
+
+
+def test_linear_kernel_matches_reference_goldens(fixtures):
+    x1, x2 = T(fixtures.raw("kern/x1")), T(fixtures.raw("kern/x2"))
+    v = torch.ones(3, dtype=torch.float64)
+    assert np.allclose(O.cov("Linear", x1, None, None, v).numpy(), fixtures.raw("kern/Linear_kx"))
+    assert np.allclose(O.cov("Linear", x1, x2, None, v).numpy(), fixtures.raw("kern/Linear_kx2"))
+    assert np.allclose(O.cov_diag("Linear", x1, v).numpy(), fixtures.raw("kern/Linear_kdiag"))
+
+
+def test_squared_distance_known_answers(fixtures):
+    """test/test_util.py:38-106: values, first derivative (-4, 0) and second derivative 2 at r^2 = 0."""
+    x1 = T([[0.0], [1.0], [2.0]])
+    x2 = T([[0.0], [2.0], [4.0]])
+    assert np.array_equal(O.sqdist(x1, x2).numpy(), fixtures.raw("pin/sqdist_values"))
+    a = T([[0.0]]).requires_grad_(True)
+    b = T([[2.0]])
+    r2 = O.sqdist(a, b)
+    (g,) = torch.autograd.grad(r2.sum(), a, create_graph=True)
+    assert g.item() == -4.0
+    a0 = T([[1.0]]).requires_grad_(True)
+    r2 = O.sqdist(a0, T([[1.0]]))
+    (g,) = torch.autograd.grad(r2.sum(), a0, create_graph=True)
+    assert g.item() == 0.0
+    (h,) = torch.autograd.grad(g.sum(), a0)
+    assert h.item() == 2.0
+
+
+def test_sparse_known_answers(fixtures):
+    """test/test_models/test_sparse_gpr.py:101,220 and the vfe_/svgp_ prediction files."""
+    x = T(fixtures.raw("sparse/x")[:, None]); y = T(fixtures.raw("sparse/y")[:, None])  # noqa: E702
+    z = T(fixtures.raw("sparse/z")[:, None]); xs = T(fixtures.raw("sparse/x_test")[:, None])  # noqa: E702
+    h = O.Hyper("Matern32", [1.0], [1.0], [1.0])
+    vfe = -O.vfe_elbo(h, x, y, z)
+    assert vfe.item() == pytest.approx(8.842242323920674)
+    assert vfe.item() == float(fixtures.raw("run/vfe_loss"))
+    mu, cov = O.vfe_predict(h, x, y, z, xs, diag=False)
+    assert mu.detach().numpy().ravel() == pytest.approx(fixtures.raw("sparse/vfe_y_mean").ravel())
+    assert cov.detach().numpy() == pytest.approx(fixtures.raw("sparse/vfe_y_cov").reshape(2, 2))
+    q_mu = T(fixtures.raw("sparse/q_mu")[:, None]); l_s = T(fixtures.raw("sparse/l_s").reshape(2, 2))  # noqa: E702
+    svgp = -O.svgp_elbo(h, x, y, z, q_mu, l_s, num_data=3)
+    assert svgp.item() == pytest.approx(9.534628739243518)
+    mu, cov = O.svgp_predict(h, z, q_mu, l_s, xs, diag=False)
+    assert mu.detach().numpy().ravel() == pytest.approx(fixtures.raw("sparse/svgp_y_mean").ravel())
+    assert cov.detach().numpy() == pytest.approx(fixtures.raw("sparse/svgp_y_cov").reshape(2, 2))
+
+
+def test_jitter_schedule():
+    """SURVEY 10 'Jitter': ones(4,4) succeeds at the first retry with exactly +1e-10; -I exhausts the schedule."""
+    L = O.chol(torch.ones(4, 4, dtype=torch.float64))
+    ref = torch.linalg.cholesky(torch.ones(4, 4, dtype=torch.float64) + 1e-10 * torch.eye(4, dtype=torch.float64))
+    assert torch.equal(L, ref)
+    with pytest.raises(RuntimeError, match="Max tries exceeded."):
+        O.chol(-torch.eye(4, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("name", [n for n in _GPR.names if int(_GPR.get(n, "n")) <= 1024])
+def test_gpr_oracle_reproduces_reference_run(name):
+    c = _GPR
+    X, Y, _ = case_inputs(c, name)
+    h = O.Hyper(str(c.get(name, "kind")), c.get(name, "ell"), c.get(name, "variance"), c.get(name, "noise"))
+    loss = -O.gpr_loglik(h, X, Y)
+    assert loss.shape == (1,)
+    loss.sum().backward()
+    assert rel_err(loss.detach().numpy(), c.get(name, "loss")) <= 1e-13
+    assert rel_err(h.raw_var.grad.numpy(), c.get(name, "g_variance")) <= 1e-11
+    assert rel_err(h.raw_ell.grad.numpy(), c.get(name, "g_length_scales")) <= 1e-11
+    assert rel_err(h.raw_noise.grad.numpy(), c.get(name, "g_noise")) <= 1e-11
+    if c.has(name, "Xs"):
+        with torch.no_grad():
+            mu, var = O.gpr_predict(h, X, Y, T(c.get(name, "Xs")), diag=True)
+        assert rel_err(mu.numpy(), c.get(name, "pred_mean")) <= 1e-12
+        assert np.abs(var.numpy() - c.get(name, "pred_var")).max() <= 1e-10
+
+
+def test_gpr_survey_loss_pins():
+    """BASELINE.md section 3 pins, measured by the survey on the unmodified reference."""
+    for n, pin in ((1024, -606.3903292756472), (2048, -1420.2752146205817)):
+        X, Y, _ = O.synth_regression(n, 8)
+        h = O.Hyper("Rbf", np.ones(8), 1.0, 0.01)
+        with torch.no_grad():
+            loss = -O.gpr_loglik(h, X, Y)
+        assert loss.item() == pytest.approx(pin, rel=1e-12)
+
+
+@pytest.mark.parametrize("name", [n for n in _VFE.names if int(_VFE.get(n, "n")) <= 2000])
+def test_vfe_oracle_reproduces_reference_run(name):
+    c = _VFE
+    X, Y, g = case_inputs(c, name)
+    Z = T(c.get(name, "Z")) if c.has(name, "Z") else O.synth_inducing(X, int(c.get(name, "m")), g)
+    h = O.Hyper(str(c.get(name, "kind")), c.get(name, "ell"), c.get(name, "variance"), c.get(name, "noise"))
+    Zp = Z.clone().requires_grad_(True)
+    loss = -O.vfe_elbo(h, X, Y, Zp)
+    loss.backward()
+    assert rel_err(loss.item(), c.get(name, "loss")) <= 1e-13
+    assert rel_err(Zp.grad.numpy(), c.get(name, "g_Z")) <= 1e-10
+    assert rel_err(h.raw_ell.grad.numpy(), c.get(name, "g_length_scales")) <= 1e-10
+
+
+@pytest.mark.parametrize("name", _SVGP.names)
+def test_svgp_oracle_reproduces_reference_run(name):
+    c = _SVGP
+    h = O.Hyper(str(c.get(name, "kind")), c.get(name, "ell"), c.get(name, "variance"), c.get(name, "noise"))
+    qm = T(c.get(name, "q_mu")).requires_grad_(True)
+    qr = T(c.get(name, "q_sqrt_raw")).requires_grad_(True)
+    Zp = T(c.get(name, "Z")).requires_grad_(True)
+    loss = -O.svgp_elbo(h, T(c.get(name, "xb")), T(c.get(name, "yb")), Zp, qm, O.lower_cholesky_transform(qr),
+                        num_data=int(c.get(name, "n")))
+    loss.backward()
+    assert rel_err(loss.item(), c.get(name, "loss")) <= 1e-13
+    assert rel_err(qm.grad.numpy(), c.get(name, "g_q_mu")) <= 1e-10
+    assert rel_err(Zp.grad.numpy(), c.get(name, "g_Z")) <= 1e-10
