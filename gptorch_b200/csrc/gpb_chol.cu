@@ -23,22 +23,77 @@ namespace gpb {
 void set_last_error_msg(const char* msg);
 
 // ================================================================================================
-// 128 x 128 diagonal block: Cholesky + inverse in shared memory (one CTA)
+// 128 x 128 diagonal block: Cholesky + inverse in shared memory (one CTA, on the critical path)
 // ================================================================================================
+// Blocked on 16 x 16 sub-blocks.  Per sub-block: warp 0 factors it and inverts it in REGISTERS (lane i owns
+// row i; pivots and columns travel by shuffles; rsqrt() replaces sqrt + divide and doubles as 1/L_kk for the
+// inverse), then all 16 warps apply the panel solve and the rank-16 trailing update with DMMA on fragments
+// read straight from shared memory (row stride 132 doubles: conflict free).  The inverse of the whole block
+// follows from the 16 x 16 inverses by block forward substitution, again on DMMA:  M_ik = I_ii L_ik, then
+// X_ij = -sum_{k=j}^{i-1} M_ik X_kj level by level (i - j = 1..7).
 constexpr int DG_THREADS = 512;
-constexpr int DG_LD = 129;
-constexpr int DG_SMEM_BYTES = (NB * DG_LD + 2 * NB) * 8 + 16;
+constexpr int DG_LD = 132;   // 132 mod 16 == 4
+constexpr int DG_SB = 16;    // sub-block
+constexpr int DG_NSB = NB / DG_SB;
+constexpr int DG_ILD = 20;   // row stride of the 16 x 16 inverse blocks (20 mod 16 == 4)
+constexpr int DG_SMEM_BYTES = (NB * DG_LD + DG_NSB * DG_SB * DG_ILD) * 8 + 16;
 
-// A: pointer to the block's (0,0) element; nb <= 128 valid rows/cols (rest is treated as identity).
-// dinv_blk: 128 x 128 (ld 128) output, inverse of the (padded) lower factor, zeros above the diagonal.
+// Warp-level Cholesky of a 16x16 block held one row per lane (lanes >= 16 carry zeros), in place; rs[k] =
+// 1/L_kk.  `bad` returns the first column (0-based) with a non-positive / NaN pivot, or -1.
+__device__ __forceinline__ void warp_potrf16(double (&a)[DG_SB], double (&rs)[DG_SB], int lane, int& bad) {
+  bad = -1;
+#pragma unroll
+  for (int k = 0; k < DG_SB; ++k) {
+    const double dk = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(dk > 0.0) && bad < 0) bad = k;
+    const double r = rsqrt(dk);
+    rs[k] = r;
+    if (lane == k) a[k] = dk * r;
+    else if (lane > k) a[k] *= r;
+    const double lk = a[k];
+#pragma unroll
+    for (int j = 0; j < DG_SB; ++j) {
+      if (j > k) {
+        const double ljk = __shfl_sync(0xffffffffu, lk, j);
+        if (lane >= j) a[j] -= lk * ljk;
+      }
+    }
+  }
+}
+
+// Inverse of the lower-triangular 16x16 block held one row per lane: lane c ends with column c in x[].
+__device__ __forceinline__ void warp_trtri16(const double (&a)[DG_SB], const double (&rs)[DG_SB], double (&x)[DG_SB],
+                                             int lane) {
+#pragma unroll
+  for (int i = 0; i < DG_SB; ++i) x[i] = (i == lane) ? rs[i] : 0.0;
+#pragma unroll
+  for (int i = 1; i < DG_SB; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DG_SB; ++k) {
+      if (k < i) {
+        const double lik = __shfl_sync(0xffffffffu, a[k], i);   // L[i][k]
+        s += lik * x[k];
+      }
+    }
+    if (i > lane) x[i] = -rs[i] * s;
+  }
+}
+
+// blockIdx.x selects the diagonal block; A0 points at element (0,0) of the matrix; j_first is the index of
+// the first diagonal block handled by this launch.
 __global__ void __launch_bounds__(DG_THREADS, 1)
-diag_block_kernel(double* __restrict__ A, long lda, int nb, double* __restrict__ dinv_blk, int* info, int j0,
+diag_block_kernel(double* __restrict__ A0, long lda, int n, double* __restrict__ dinv, int* info, int j_first,
                   int do_factor) {
   extern __shared__ double dg_smem[];
-  double* S = dg_smem;                 // [128][129]; lower: L ; S[c][i+1] (i>c): inverse entry (i,c)
-  double* rsq = S + NB * DG_LD;        // 1/sqrt(pivot_k)
-  double* invd = rsq + NB;             // 1/L_kk
-  const int t = threadIdx.x;
+  double* S = dg_smem;                     // [128][132]
+  double* Ib = S + NB * DG_LD;             // [8][16][20]: inverses of the diagonal 16x16 sub-blocks
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int r8 = lane >> 2, kk = lane & 3;
+  const int j0 = (j_first + blockIdx.x) * NB;
+  const int nb = min(NB, n - j0);
+  double* A = A0 + static_cast<long>(j0) * lda + j0;
+  double* dinv_blk = dinv + static_cast<long>(j0) * NB;
 
   for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
@@ -49,57 +104,79 @@ diag_block_kernel(double* __restrict__ A, long lda, int nb, double* __restrict__
     }
     S[r * DG_LD + c] = v;
   }
+  __syncthreads();
 
-  const int row = t >> 2, q = t & 3;
-  if (do_factor) {
-    // Right-looking, one barrier per column.  Column k is never rescaled in place (other rows read it
-    // un-scaled during step k); the scale 1/sqrt(pivot) is applied on the fly and once more at the end.
-    for (int k = 0; k < NB; ++k) {
-      __syncthreads();
-      const double d = S[k * DG_LD + k];
-      if (!(d > 0.0)) {
-        // LAPACK potrf: first non-positive (or NaN) pivot -> info = its 1-based index; keep going with NaNs.
-        if (t == 0 && k < nb && atomicCAS(info, 0, j0 + k + 1) == 0) { /* recorded */ }
-      }
-      const double rs = 1.0 / sqrt(d);
-      if (t == 0) rsq[k] = rs;
-      if (row > k) {
-        const double lik = S[row * DG_LD + k] * rs;
-        for (int j = k + 1 + q; j <= row; j += 4) {
-          const double ljk = S[j * DG_LD + k] * rs;
-          S[row * DG_LD + j] -= lik * ljk;
+  for (int b = 0; b < DG_NSB; ++b) {
+    const int o = b * DG_SB;
+    // ---- (a) one warp: factor + invert the 16x16 diagonal sub-block in registers --------------------
+    if (warp == 0) {
+      double a[DG_SB], rs[DG_SB], x[DG_SB];
+#pragma unroll
+      for (int j = 0; j < DG_SB; ++j) a[j] = (lane < DG_SB && j <= lane) ? S[(o + lane) * DG_LD + o + j] : 0.0;
+      if (do_factor) {
+        int bad;
+        warp_potrf16(a, rs, lane, bad);
+        if (bad >= 0 && lane == 0 && o + bad < nb) atomicCAS(info, 0, j0 + o + bad + 1);
+        if (lane < DG_SB) {
+#pragma unroll
+          for (int j = 0; j < DG_SB; ++j)
+            if (j <= lane) S[(o + lane) * DG_LD + o + j] = a[j];
         }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DG_SB; ++k) rs[k] = 1.0 / __shfl_sync(0xffffffffu, a[k], k);
+      }
+      warp_trtri16(a, rs, x, lane);
+      if (lane < DG_SB) {
+#pragma unroll
+        for (int i = 0; i < DG_SB; ++i) Ib[(b * DG_SB + i) * DG_ILD + lane] = x[i];
+      }
+    }
+    if (!do_factor) continue;   // inverse-only: the sub-block inverses are all that phase 1 provides
+    __syncthreads();
+    const int R0 = o + DG_SB;
+    // ---- (b) panel: rows below the sub-block  <-  rows * I_bb^T  (strips of 8 rows, one per warp) ------
+    for (int strip = warp; strip < (NB - R0) / 8; strip += DG_THREADS / 32) {
+      const int row = R0 + 8 * strip + r8;
+      double af[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) af[ks] = S[row * DG_LD + o + 4 * ks + kk];
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double bf = Ib[(b * DG_SB + 8 * jn + r8) * DG_ILD + 4 * ks + kk];
+          dmma884(acc[jn][0], acc[jn][1], af[ks], bf);
+        }
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn) {
+        S[row * DG_LD + o + 8 * jn + 2 * kk] = acc[jn][0];
+        S[row * DG_LD + o + 8 * jn + 2 * kk + 1] = acc[jn][1];
       }
     }
     __syncthreads();
-    // final scaling: L[i][k] = S[i][k] * rsq[k] (i > k), L[k][k] = sqrt(pivot) = pivot * rsq[k]
-    for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
-      const int r = idx >> 7, c = idx & 127;
-      if (c <= r) S[r * DG_LD + c] *= rsq[c];
-    }
-  }
-  __syncthreads();
-  if (t < NB) invd[t] = 1.0 / S[t * DG_LD + t];
-  __syncthreads();
-
-  // ---- inverse: 4 lanes per column c, forward substitution  x_i = -(sum_{k=c}^{i-1} L_ik x_k) / L_ii ------
-  {
-    const int c = row;
-    const int cmin = (t >> 5) * 8;  // smallest column handled by this warp (uniform loop bounds)
-    const double xc = invd[c];
-    for (int i = cmin + 1; i < NB; ++i) {
-      double part = 0.0;
-      if (i > c) {
-        for (int k = c + q; k < i; k += 4) {
-          const double xk = (k == c) ? xc : S[c * DG_LD + k + 1];
-          part += S[i * DG_LD + k] * xk;
+    // ---- (c) trailing update: lower 8x8 tiles of S[R0:, R0:] -= P P^T, K = 16 -------------------------
+    {
+      const int T = (NB - R0) / 8;
+      const int ntile = T * (T + 1) / 2;
+      for (int tile = warp; tile < ntile; tile += DG_THREADS / 32) {
+        int ti = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+        while (ti * (ti + 1) / 2 > tile) --ti;
+        const int tj = tile - ti * (ti + 1) / 2;
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double af = S[(R0 + 8 * ti + r8) * DG_LD + o + 4 * ks + kk];
+          const double bf = S[(R0 + 8 * tj + r8) * DG_LD + o + 4 * ks + kk];
+          dmma884(acc0, acc1, af, bf);
         }
+        double* c = &S[(R0 + 8 * ti + r8) * DG_LD + R0 + 8 * tj + 2 * kk];
+        c[0] -= acc0;
+        c[1] -= acc1;
       }
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      if (i > c && q == 0) S[c * DG_LD + i + 1] = -part * invd[i];
-      __syncwarp();
     }
+    __syncthreads();
   }
   __syncthreads();
 
@@ -109,75 +186,92 @@ diag_block_kernel(double* __restrict__ A, long lda, int nb, double* __restrict__
       if (r < nb && c <= r) A[static_cast<long>(r) * lda + c] = S[r * DG_LD + c];
     }
   }
+
+  // ---- phase 2: X = L^-1 from the sub-block inverses ----------------------------------------------------
+  // step A: M_ik = I_ii L_ik for every strictly-lower 16x16 block (28 blocks x 4 tiles of 8x8), in place.
+  {
+    constexpr int NTILE = (DG_NSB * (DG_NSB - 1) / 2) * 4;   // 112
+    double m0[NTILE / 16], m1[NTILE / 16];
+#pragma unroll
+    for (int q = 0; q < NTILE / 16; ++q) {
+      const int tile = warp + 16 * q;
+      const int blk = tile >> 2, tm = (tile >> 1) & 1, tn = tile & 1;
+      int bi = static_cast<int>((sqrtf(8.0f * blk + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+      while (bi * (bi + 1) / 2 > blk) --bi;
+      const int bk = blk - bi * (bi + 1) / 2;
+      const int i = bi + 1;   // block row 1..7, block col bk 0..i-1
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const double af = Ib[(i * DG_SB + 8 * tm + r8) * DG_ILD + 4 * ks + kk];
+        const double bf = S[(i * DG_SB + 4 * ks + kk) * DG_LD + bk * DG_SB + 8 * tn + r8];
+        dmma884(acc0, acc1, af, bf);
+      }
+      m0[q] = acc0;
+      m1[q] = acc1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NTILE / 16; ++q) {
+      const int tile = warp + 16 * q;
+      const int blk = tile >> 2, tm = (tile >> 1) & 1, tn = tile & 1;
+      int bi = static_cast<int>((sqrtf(8.0f * blk + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+      while (bi * (bi + 1) / 2 > blk) --bi;
+      const int bk = blk - bi * (bi + 1) / 2;
+      const int i = bi + 1;
+      double* c = &S[(i * DG_SB + 8 * tm + r8) * DG_LD + bk * DG_SB + 8 * tn + 2 * kk];
+      c[0] = m0[q];
+      c[1] = m1[q];
+    }
+    __syncthreads();
+  }
+  // levels d = i - j: X_ij = -sum_{k=j}^{i-1} M_ik X_kj, with X_jj = I_jj and X_kj (k > j) kept at the mirrored
+  // (upper) block position S[16 j + . ][16 k + . ].
+  for (int d = 1; d < DG_NSB; ++d) {
+    const int ntile = (DG_NSB - d) * 4;
+    for (int tile = warp; tile < ntile; tile += DG_THREADS / 32) {
+      const int j = tile >> 2, tm = (tile >> 1) & 1, tn = tile & 1;
+      const int i = j + d;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int k = j; k < i; ++k) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const double af = S[(i * DG_SB + 8 * tm + r8) * DG_LD + k * DG_SB + 4 * ks + kk];   // M_ik
+          const double bf = (k == j) ? Ib[(j * DG_SB + 4 * ks + kk) * DG_ILD + 8 * tn + r8]
+                                     : S[(j * DG_SB + 4 * ks + kk) * DG_LD + k * DG_SB + 8 * tn + r8];  // X_kj
+          dmma884(acc0, acc1, af, bf);
+        }
+      }
+      double* c = &S[(j * DG_SB + 8 * tm + r8) * DG_LD + i * DG_SB + 8 * tn + 2 * kk];
+      c[0] = -acc0;
+      c[1] = -acc1;
+    }
+    __syncthreads();
+  }
+
   for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
     const int r = idx >> 7, c = idx & 127;
+    const int bi = r >> 4, bj = c >> 4;
     double v = 0.0;
-    if (c < r) v = S[c * DG_LD + r + 1];
-    else if (c == r) v = invd[r];
+    if (bi == bj) v = Ib[(bi * DG_SB + (r & 15)) * DG_ILD + (c & 15)];
+    else if (bi > bj) v = S[(bj * DG_SB + (r & 15)) * DG_LD + bi * DG_SB + (c & 15)];
     dinv_blk[r * NB + c] = v;
   }
 }
 
-static int launch_diag_block(double* A, long lda, int nb, double* dinv_blk, int* info, int j0, int do_factor,
-                             cudaStream_t stream) {
+static int launch_diag_blocks(double* A0, long lda, int n, double* dinv, int* info, int j_first, int nblocks,
+                              int do_factor, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     GPB_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
     attr_set = true;
   }
-  diag_block_kernel<<<1, DG_THREADS, DG_SMEM_BYTES, stream>>>(A, lda, nb, dinv_blk, info, j0, do_factor);
+  diag_block_kernel<<<nblocks, DG_THREADS, DG_SMEM_BYTES, stream>>>(A0, lda, n, dinv, info, j_first, do_factor);
   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
-}
-
-// Batched variant for gpb_tri_diag_inverse (no factorisation): one CTA per diagonal block.
-__global__ void __launch_bounds__(DG_THREADS, 1)
-diag_inverse_batched_kernel(const double* __restrict__ L, long ldl, int n, double* __restrict__ dinv) {
-  extern __shared__ double dg_smem[];
-  double* S = dg_smem;
-  double* invd = S + NB * DG_LD + NB;
-  const int t = threadIdx.x;
-  const int j0 = blockIdx.x * NB;
-  const int nb = min(NB, n - j0);
-  const double* A = L + static_cast<long>(j0) * ldl + j0;
-  for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    double v = 0.0;
-    if (c <= r) {
-      if (r < nb) v = A[static_cast<long>(r) * ldl + c];
-      else v = (r == c) ? 1.0 : 0.0;
-    }
-    S[r * DG_LD + c] = v;
-  }
-  __syncthreads();
-  if (t < NB) invd[t] = 1.0 / S[t * DG_LD + t];
-  __syncthreads();
-  const int c = t >> 2, q = t & 3;
-  const int cmin = (t >> 5) * 8;
-  const double xc = invd[c];
-  for (int i = cmin + 1; i < NB; ++i) {
-    double part = 0.0;
-    if (i > c) {
-      for (int k = c + q; k < i; k += 4) {
-        const double xk = (k == c) ? xc : S[c * DG_LD + k + 1];
-        part += S[i * DG_LD + k] * xk;
-      }
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if (i > c && q == 0) S[c * DG_LD + i + 1] = -part * invd[i];
-    __syncwarp();
-  }
-  __syncthreads();
-  double* out = dinv + static_cast<long>(j0) * NB;
-  for (int idx = t; idx < NB * NB; idx += DG_THREADS) {
-    const int r = idx >> 7, cc = idx & 127;
-    double v = 0.0;
-    if (cc < r) v = S[cc * DG_LD + r + 1];
-    else if (cc == r) v = invd[r];
-    out[r * NB + cc] = v;
-  }
 }
 
 // ================================================================================================
@@ -211,6 +305,7 @@ static int trsm_right_rec(CholCtx& c, int r0, int m, int c0, int n) {
     g.ldc = c.lda;
     g.ax = c0; g.ay = r0;
     g.bx = 0; g.by = c0;
+    g.flags = GF_ROWS_INPLACE;
     return gemm_launch(GEMM_NT, c.mapA128, c.mapD128, g, c.stream);
   }
   const int n1 = split_point(n), n2 = n - n1;
@@ -230,10 +325,7 @@ static int trsm_right_rec(CholCtx& c, int r0, int m, int c0, int n) {
 
 static int potrf_rec(CholCtx& c, int j0, int n) {
   if (n <= 0) return GPB_OK;
-  if (n <= NB) {
-    return launch_diag_block(c.A + static_cast<long>(j0) * c.lda + j0, c.lda, n, c.dinv + static_cast<long>(j0) * NB,
-                             c.info, j0, 1, c.stream);
-  }
+  if (n <= NB) return launch_diag_blocks(c.A, c.lda, c.n, c.dinv, c.info, j0 / NB, 1, 1, c.stream);
   const int n1 = split_point(n), n2 = n - n1;
   int rc = potrf_rec(c, j0, n1);
   if (rc) return rc;
@@ -259,9 +351,9 @@ int potrf_lower(double* A, int n, long lda, double* dinv, int* info, cudaStream_
   if (!A || !dinv || !info || lda < n) return GPB_ERR_BADARG;
   CholCtx c;
   c.A = A; c.lda = lda; c.n = n; c.dinv = dinv; c.info = info; c.stream = stream;
-  int rc = make_tmap_f64(&c.mapA128, A, n, n, lda, 128);
+  int rc = make_tmap_f64(&c.mapA128, A, n, n, lda, 32);
   if (rc) return rc;
-  rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 128);
+  rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 32);
   if (rc) return rc;
   return potrf_rec(c, 0, n);
 }
@@ -287,6 +379,7 @@ static int trsm_panel_rec(TrsmCtx& c, int c0, int n) {
     g.C = c.X + c0; g.ldc = c.ldx;
     g.ax = c0; g.ay = 0;
     g.bx = 0; g.by = c0;
+    g.flags = GF_ROWS_INPLACE;
     return gemm_launch(GEMM_NT, c.mapX128, c.mapD128, g, c.stream);
   }
   const int n1 = split_point(n), n2 = n - n1;
@@ -309,11 +402,11 @@ int trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* 
   if (!L || !dinv || !X || ldl < n || ldx < n) return GPB_ERR_BADARG;
   TrsmCtx c;
   c.X = X; c.ldx = ldx; c.m = m; c.stream = stream;
-  int rc = make_tmap_f64(&c.mapX128, X, m, n, ldx, 128);
+  int rc = make_tmap_f64(&c.mapX128, X, m, n, ldx, 32);
   if (rc) return rc;
-  rc = make_tmap_f64(&c.mapL128, L, n, n, ldl, 128);
+  rc = make_tmap_f64(&c.mapL128, L, n, n, ldl, 32);
   if (rc) return rc;
-  rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 128);
+  rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 32);
   if (rc) return rc;
   return trsm_panel_rec(c, 0, n);
 }
@@ -321,17 +414,8 @@ int trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* 
 int tri_diag_inverse(const double* L, int n, long ldl, double* dinv, cudaStream_t stream) {
   if (n <= 0) return GPB_OK;
   if (!L || !dinv || ldl < n) return GPB_ERR_BADARG;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GPB_CUDA_CHECK(cudaFuncSetAttribute(diag_inverse_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        DG_SMEM_BYTES));
-    attr_set = true;
-  }
   const int nblk = (n + NB - 1) / NB;
-  diag_inverse_batched_kernel<<<nblk, DG_THREADS, DG_SMEM_BYTES, stream>>>(L, ldl, n, dinv);
-  count_launch();
-  GPB_CUDA_CHECK(cudaGetLastError());
-  return GPB_OK;
+  return launch_diag_blocks(const_cast<double*>(L), ldl, n, dinv, nullptr, 0, nblk, 0, stream);
 }
 
 // ================================================================================================
@@ -382,7 +466,7 @@ int trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace,
     GPB_CUDA_CHECK(cudaGetLastError());
   }
   CUtensorMap mapA128, mapA16;
-  int rc = make_tmap_f64(&mapA128, A, n, n, lda, 128);
+  int rc = make_tmap_f64(&mapA128, A, n, n, lda, 32);
   if (rc) return rc;
   rc = make_tmap_f64(&mapA16, A, n, n, lda, 16);
   if (rc) return rc;
@@ -396,7 +480,7 @@ int trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace,
     CUtensorMap mapW128;
     const int nprob = nfull + (n2_last > 0 ? 1 : 0);
     if (nprob == 0) continue;
-    rc = make_tmap_f64(&mapW128, W, static_cast<long>(nprob) * s, s, s, 128);
+    rc = make_tmap_f64(&mapW128, W, static_cast<long>(nprob) * s, s, s, 32);
     if (rc) return rc;
     for (int pass = 0; pass < 2; ++pass) {
       const int batch = pass == 0 ? nfull : (n2_last > 0 ? 1 : 0);
@@ -441,7 +525,7 @@ int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_bl
   int rc = trtri_upper(A, n, lda, dinv, workspace, workspace_bytes, stream);
   if (rc) return rc;
   CUtensorMap mapA128;
-  rc = make_tmap_f64(&mapA128, A, n, n, lda, 128);
+  rc = make_tmap_f64(&mapA128, A, n, n, lda, 32);
   if (rc) return rc;
   // Kinv = T T^T: strictly-lower blocks in place, diagonal blocks to kdiag_blocks.
   GemmArgs g;

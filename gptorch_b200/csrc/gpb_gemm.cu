@@ -5,9 +5,10 @@
 // L^-T L^-1 product that replace autograd's CholeskyBackward0, and the
 // Kuf-panel products of the sparse models (gptorch/models/sparse_gpr.py:132-137).
 //
-// Design (B200): CTA tile 128x128, K-chunk 16 (one 128-byte swizzled TMA row per operand row), ring of
-// GEMM_STAGES stages, 8 consumer warps (2 x 4, warp tile 64 x 32 = 8 x 4 DMMA fragments, 64 fp64
-// accumulators per thread) + 1 producer warp whose elected lane issues cp.async.bulk.tensor.  FP64 peak
+// Design (B200): CTA tile 128x128 (64x64 for launches too small to fill the chip), K-chunk 16 (one 128-byte
+// swizzled TMA row per operand row), ring of 5-6 stages, 8 consumer warps (2 x 4, warp tile 64 x 32 = 8 x 4
+// DMMA fragments, 64 fp64 accumulators per thread) + 1 producer warp whose elected lane issues
+// cp.async.bulk.tensor.  FP64 peak
 // on B200 is 64 FMA/clk/SM for DFMA and DMMA alike (measured 37.0 TFLOP/s); DMMA needs 8x fewer issue
 // slots and 12 LDS.64 per 32 DMMA, so shared-memory bandwidth and issue are far from limiting and the
 // k-permuted fragment addressing below is bank-conflict free under SWIZZLE_128B.
@@ -15,14 +16,29 @@
 
 namespace gpb {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int GEMM_STAGES = 5;
-constexpr int A_TILE_BYTES = BM * BK * 8;  // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 8;  // 16 KB
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-constexpr int GEMM_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BK = 16;                 // k-chunk: one 128-byte (swizzled) row per operand row
+constexpr int NT_BOX_ROWS = 32;        // rows of a K-contiguous TMA box (all NT/NN-A tensor maps use this)
+
+// Tile configurations.  L: the throughput shape (1 CTA/SM, 64 accumulators per thread).  S: for launches that
+// would leave most SMs idle with 128x128 tiles (the latency-bound small products at the bottom of the
+// Cholesky / TRSM recursions) -- 4x the CTAs, each 1/4 of the work.
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+struct GemmCfg {
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_;
+  static constexpr int MI = WM / 8, NI = WN / 8;
+  static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+  static constexpr int CONSUMER_WARPS = WARPS_M * WARPS_N;
+  static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+  static constexpr int A_TILE_BYTES = BM * BK * 8;
+  static constexpr int B_TILE_BYTES = BN * BK * 8;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+using CfgL = GemmCfg<128, 128, 64, 32, 5>;
+using CfgS = GemmCfg<64, 64, 32, 32, 6>;
+// T: row strips for the in-place right-TRSM base case (N <= 128 = BN: one CTA owns all columns of its rows, so
+// every TMA read of those rows completes before the CTA's own epilogue overwrites them).
+using CfgT = GemmCfg<32, 128, 32, 32, 6>;
 
 struct GemmKParams {
   int M, N, K;
@@ -41,15 +57,17 @@ __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t col) {
   return row * 128u + ((((col >> 1) ^ (row & 7u)) << 4) | ((col & 1u) << 3));
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int MODE, class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const GemmKParams p) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, MI = Cfg::MI, NI = Cfg::NI;
+  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, A_TILE_BYTES = Cfg::A_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al + GEMM_STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -77,18 +95,19 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (p.flags & GF_KLO_N) k_lo = max(k_lo, n0);
   if (p.flags & GF_KHI_M) k_hi = min(k_hi, m0 + BM);
   if (p.flags & GF_KHI_N) k_hi = min(k_hi, n0 + BN);
+  k_lo &= ~(BK - 1);
   const int nk = k_hi > k_lo ? (k_hi - k_lo + BK - 1) / BK : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
+      mbar_init(&empty_bar[s], Cfg::CONSUMER_WARPS);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == GEMM_CONSUMER_WARPS) {
+  if (warp == Cfg::CONSUMER_WARPS) {
     // =============================== TMA producer ==============================================
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
@@ -96,8 +115,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int ax = p.ax + bz * p.dax, ay = p.ay + bz * p.day;
       const int bx = p.bx + bz * p.dbx, by = p.by + bz * p.dby;
       for (int it = 0; it < nk; ++it) {
-        const int s = it % GEMM_STAGES;
-        const uint32_t ph = (it / GEMM_STAGES) & 1;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         uint8_t* a_dst = smem_al + s * STAGE_BYTES;
@@ -107,10 +126,14 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < BM / 16; ++j) tma_load_2d(a_dst + j * 2048, &mapA, ax + m0 + 16 * j, ay + k, &full_bar[s]);
         } else {
-          tma_load_2d(a_dst, &mapA, ax + k, ay + m0, &full_bar[s]);
+#pragma unroll
+          for (int j = 0; j < BM / NT_BOX_ROWS; ++j)
+            tma_load_2d(a_dst + j * (NT_BOX_ROWS * 128), &mapA, ax + k, ay + m0 + NT_BOX_ROWS * j, &full_bar[s]);
         }
         if (MODE == GEMM_NT) {
-          tma_load_2d(b_dst, &mapB, bx + k, by + n0, &full_bar[s]);
+#pragma unroll
+          for (int j = 0; j < BN / NT_BOX_ROWS; ++j)
+            tma_load_2d(b_dst + j * (NT_BOX_ROWS * 128), &mapB, bx + k, by + n0 + NT_BOX_ROWS * j, &full_bar[s]);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 16; ++j) tma_load_2d(b_dst + j * 2048, &mapB, bx + n0 + 16 * j, by + k, &full_bar[s]);
@@ -121,18 +144,18 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 
   // ================================= DMMA consumers ==============================================
-  const int wm = warp & 1, wn = warp >> 1;  // 2 x 4 warps, warp tile 64 x 32
+  const int wm = warp % Cfg::WARPS_M, wn = warp / Cfg::WARPS_M;
   const int r = lane >> 2, kk = lane & 3;
 
-  double acc[8][4][2];
+  double acc[MI][NI][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // Per-lane fragment offsets (bytes, relative to the A / B tile of a stage) for the 4 k4-steps.
   //  K-contiguous operand tile [row][16 k]:   element (row, kcol) with kcol = 2s + (kk&1) + 8(kk>>1)
-  //  MN-contiguous operand tile [16 k][16 x] x 8 sub-boxes: element (krow, x) with
+  //  MN-contiguous operand tile [16 k][16 x] x (B?/16) sub-boxes: element (krow, x) with
   //     krow = 2kk + (s&1) + 8(s>>1)  (TN: both operands)   or   krow = kcol above (NN: B operand).
   uint32_t a_off[4], b_off[4];
 #pragma unroll
@@ -140,32 +163,32 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const uint32_t kcol_nt = 2 * s + (kk & 1) + 8 * (kk >> 1);
     const uint32_t krow_tn = 2 * kk + (s & 1) + 8 * (s >> 1);
     if (MODE == GEMM_TN) {
-      const uint32_t ml = wm * 64 + r;  // + 8i added below (i even/odd changes the sub-box column half)
+      const uint32_t ml = wm * WM + r;  // + 8i added below (i even/odd changes the sub-box column half)
       a_off[s] = (ml >> 4) * 2048u + swz(krow_tn, ml & 15u);
-      const uint32_t nl = wn * 32 + r;
+      const uint32_t nl = wn * WN + r;
       b_off[s] = (nl >> 4) * 2048u + swz(krow_tn, nl & 15u);
     } else {
-      a_off[s] = swz(wm * 64 + r, kcol_nt);
+      a_off[s] = swz(wm * WM + r, kcol_nt);
       if (MODE == GEMM_NT) {
-        b_off[s] = swz(wn * 32 + r, kcol_nt);
+        b_off[s] = swz(wn * WN + r, kcol_nt);
       } else {
-        const uint32_t nl = wn * 32 + r;
+        const uint32_t nl = wn * WN + r;
         b_off[s] = (nl >> 4) * 2048u + swz(kcol_nt, nl & 15u);
       }
     }
   }
 
   for (int it = 0; it < nk; ++it) {
-    const int s = it % GEMM_STAGES;
-    const uint32_t ph = (it / GEMM_STAGES) & 1;
+    const int s = it % STAGES;
+    const uint32_t ph = (it / STAGES) & 1;
     mbar_wait(&full_bar[s], ph);
     const uint32_t a_base = smem_base + s * STAGE_BYTES;
     const uint32_t b_base = a_base + A_TILE_BYTES;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      double a[8], b[4];
+      double a[MI], b[NI];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < MI; ++i) {
         uint32_t off;
         if (MODE == GEMM_TN) {
           // rows 8i of the warp tile: i odd -> columns 8..15 of the sub-box (chunk index + 4), i>>1 -> next sub-box
@@ -177,7 +200,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         a[i] = ld_shared_f64(a_base + off);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NI; ++j) {
         uint32_t off;
         if (MODE == GEMM_NT) {
           off = b_off[ks] + j * 1024u;
@@ -188,9 +211,9 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         b[j] = ld_shared_f64(b_base + off);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -200,20 +223,20 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   double* Cb = p.C + static_cast<long>(bz) * p.c_batch;
   long ldc = p.ldc;
   int col_shift = 0;
-  if ((p.flags & GF_DIAG_TO_WS) && tm == tn) {
+  if ((p.flags & GF_DIAG_TO_WS) && (m0 / NB) == (n0 / NB)) {
     Cb = p.Cdiag;
     ldc = p.ldd;
-    col_shift = n0;
+    col_shift = (n0 / NB) * NB;
   }
   const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = m0 + wm * 64 + 8 * i + r;
+  for (int i = 0; i < MI; ++i) {
+    const int row = m0 + wm * WM + 8 * i + r;
     if (row >= p.M) continue;
     double* crow = Cb + static_cast<long>(row) * ldc - col_shift;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + wn * 32 + 8 * j + 2 * kk;
+    for (int j = 0; j < NI; ++j) {
+      const int col = n0 + wn * WN + 8 * j + 2 * kk;
       if (col + 1 < p.N) {
         double2* ptr = reinterpret_cast<double2*>(crow + col);
         double2 v;
@@ -235,20 +258,44 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
-template <int MODE>
-static int launch_mode(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmKParams& kp, int ntiles, int batch,
-                       cudaStream_t stream) {
+template <int MODE, class Cfg>
+static int launch_cfg(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmKParams kp, const GemmArgs& a,
+                      cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    GPB_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        GEMM_SMEM_BYTES));
+    GPB_CUDA_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<MODE, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(ntiles, batch, 1);
-  gemm_dmma_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(mapA, mapB, kp);
+  kp.tiles_m = (a.M + Cfg::BM - 1) / Cfg::BM;
+  kp.tiles_n = (a.N + Cfg::BN - 1) / Cfg::BN;
+  int ntiles;
+  if (a.flags & GF_LOWER_TILES) {
+    if (kp.tiles_m != kp.tiles_n) return GPB_ERR_BADARG;
+    ntiles = kp.tiles_m * (kp.tiles_m + 1) / 2;
+  } else {
+    ntiles = kp.tiles_m * kp.tiles_n;
+  }
+  dim3 grid(ntiles, a.batch, 1);
+  gemm_dmma_kernel<MODE, Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, kp);
   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
+}
+
+template <int MODE>
+static int launch_mode(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmKParams& kp, const GemmArgs& a,
+                       cudaStream_t stream) {
+  // 128x128 tiles unless that would occupy fewer than ~half of the 148 SMs.
+  const long t128 = static_cast<long>((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch;
+  const long tiles = (a.flags & GF_LOWER_TILES) ? (t128 + a.batch * ((a.M + 127) / 128)) / 2 : t128;
+  if (a.flags & GF_ROWS_INPLACE) {
+    if (a.N > 128) return GPB_ERR_BADARG;
+    if (tiles <= GEMM_SMALL_TILE_THRESHOLD) return launch_cfg<MODE, CfgT>(mapA, mapB, kp, a, stream);
+    return launch_cfg<MODE, CfgL>(mapA, mapB, kp, a, stream);
+  }
+  if (tiles <= GEMM_SMALL_TILE_THRESHOLD) return launch_cfg<MODE, CfgS>(mapA, mapB, kp, a, stream);
+  return launch_cfg<MODE, CfgL>(mapA, mapB, kp, a, stream);
 }
 
 int gemm_launch(GemmMode mode, const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmArgs& a,
@@ -264,20 +311,12 @@ int gemm_launch(GemmMode mode, const CUtensorMap& mapA, const CUtensorMap& mapB,
   kp.ax = a.ax; kp.ay = a.ay; kp.bx = a.bx; kp.by = a.by;
   kp.dax = a.dax; kp.day = a.day; kp.dbx = a.dbx; kp.dby = a.dby;
   kp.flags = a.flags;
-  kp.tiles_m = (a.M + BM - 1) / BM;
-  kp.tiles_n = (a.N + BN - 1) / BN;
-  int ntiles;
-  if (a.flags & GF_LOWER_TILES) {
-    if (kp.tiles_m != kp.tiles_n) return GPB_ERR_BADARG;
-    ntiles = kp.tiles_m * (kp.tiles_m + 1) / 2;
-  } else {
-    ntiles = kp.tiles_m * kp.tiles_n;
-  }
+  kp.tiles_m = kp.tiles_n = 0;
   if ((a.flags & GF_DIAG_TO_WS) && (a.Cdiag == nullptr || (a.ldd & 1))) return GPB_ERR_BADARG;
   switch (mode) {
-    case GEMM_NT: return launch_mode<GEMM_NT>(mapA, mapB, kp, ntiles, a.batch, stream);
-    case GEMM_TN: return launch_mode<GEMM_TN>(mapA, mapB, kp, ntiles, a.batch, stream);
-    case GEMM_NN: return launch_mode<GEMM_NN>(mapA, mapB, kp, ntiles, a.batch, stream);
+    case GEMM_NT: return launch_mode<GEMM_NT>(mapA, mapB, kp, a, stream);
+    case GEMM_TN: return launch_mode<GEMM_TN>(mapA, mapB, kp, a, stream);
+    case GEMM_NN: return launch_mode<GEMM_NN>(mapA, mapB, kp, a, stream);
   }
   return GPB_ERR_BADARG;
 }

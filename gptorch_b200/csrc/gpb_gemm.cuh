@@ -16,7 +16,8 @@ enum : unsigned {
   GF_KHI_M = 4u,         // k range ends   at the tile's last row + 1  (operand zero for k >= m0 + BM)
   GF_KLO_N = 8u,         // same, keyed on the tile's column range
   GF_KHI_N = 16u,
-  GF_DIAG_TO_WS = 32u,   // diagonal tiles are written to Cdiag (row m, col n - m0) instead of C
+  GF_DIAG_TO_WS = 32u,   // tiles in a diagonal 128-block are written to Cdiag (row m, col n - block start)
+  GF_ROWS_INPLACE = 64u, // C overwrites the rows of A it is computed from (N <= 128): never split a row block over CTAs
 };
 
 struct GemmArgs {
@@ -34,12 +35,14 @@ struct GemmArgs {
   int batch = 1;
 };
 
-// Tensor maps: NT operands need box rows = 128, TN/NN "k-row" operands need box rows = 16.
-// A for NT/NN: box 128; A for TN: box 16; B for NT: box 128; B for TN/NN: box 16.
+// Tensor maps: K-contiguous operands (A of NT/NN, B of NT) use boxes of 32 rows x 16 columns, MN-contiguous
+// operands (A of TN, B of TN/NN) boxes of 16 x 16.  Launches with at most GEMM_SMALL_TILE_THRESHOLD 128x128
+// tiles run with 64x64 tiles instead (4x the CTAs).
+constexpr int GEMM_SMALL_TILE_THRESHOLD = 64;
 int gemm_launch(GemmMode mode, const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmArgs& args,
                 cudaStream_t stream);
 
-inline int gemm_box_rows_a(GemmMode m) { return m == GEMM_TN ? 16 : 128; }
-inline int gemm_box_rows_b(GemmMode m) { return m == GEMM_NT ? 128 : 16; }
+inline int gemm_box_rows_a(GemmMode m) { return m == GEMM_TN ? 16 : 32; }
+inline int gemm_box_rows_b(GemmMode m) { return m == GEMM_NT ? 32 : 16; }
 
 }  // namespace gpb

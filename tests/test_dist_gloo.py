@@ -1,0 +1,95 @@
+"""World-size-2 gloo tests (CPU) of the multi-process host logic: row sharding, the flat gradient all-reduce
+used for data-parallel SVGP, `distribute()` bookkeeping and the sufficient-statistics identity the N-sharded
+VFE relies on (sum of shard statistics == full statistics, checked with the oracle)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def _shard_and_reduce(rank, world):
+    from gptorch_b200 import dist as gd, settings, kernels
+    from gptorch_b200.models import VFE
+    settings.set_default_device("cpu")
+    n = 101
+    lo, hi = gd.shard_rows(n, rank, world)
+    rng = np.random.RandomState(0)
+    X, Y = rng.rand(n, 2), rng.rand(n, 1)
+    model = VFE(X[lo:hi], Y[lo:hi], kernels.Rbf(2), inducing_points=rng.rand(4, 2))
+    model.distribute()
+    # a fake local gradient: rank-dependent, summed by the flat all-reduce
+    for i, p in enumerate(q for q in model.parameters() if q.requires_grad):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    gd.allreduce_grads(model)
+    grads = [p.grad.flatten()[0].item() for p in model.parameters() if p.requires_grad]
+    tmax = gd.max_over_ranks(10.0 + rank, torch.device("cpu"))
+    return (lo, hi, model.num_data, grads, tmax)
+
+
+def test_row_sharding_and_grad_allreduce():
+    out = _run(_shard_and_reduce)
+    (lo0, hi0, n0, g0, t0), (lo1, hi1, n1, g1, t1) = out
+    assert (lo0, hi0, lo1, hi1) == (0, 51, 51, 101)
+    assert n0 == n1 == 101                       # distribute(): global number of data
+    assert g0 == g1 and g0[0] == 3.0 and g0[1] == 6.0   # (1 + 2) * (i + 1)
+    assert t0 == t1 == 11.0
+
+
+def test_shard_rows_partitions():
+    from gptorch_b200.dist import shard_rows
+    for n, w in ((10, 3), (7, 8), (1000003, 8), (0, 2)):
+        spans = [shard_rows(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _vfe_stats_identity(rank, world):
+    """sum_r (A_r A_r^T, A_r Y_r) over row shards equals the full-data statistics: the VFE all-reduce point."""
+    from oracle import gp_oracle as O
+    from gptorch_b200.dist import shard_rows
+    X, Y, g = O.synth_regression(400, 3)
+    Z = O.synth_inducing(X, 12, g)
+    h = O.Hyper("Matern32", [0.7, 0.9, 1.1], [1.3], [0.05])
+    with torch.no_grad():
+        L = O.chol(h.K(Z))
+        lo, hi = shard_rows(400, rank, world)
+        A = O.tri_solve(h.K(Z, X[lo:hi]), L)
+        stats = torch.cat([(A @ A.t()).reshape(-1), (A @ Y[lo:hi]).reshape(-1), Y[lo:hi].pow(2).sum().reshape(1)])
+        dist.all_reduce(stats)
+        Afull = O.tri_solve(h.K(Z, X), L)
+        full = torch.cat([(Afull @ Afull.t()).reshape(-1), (Afull @ Y).reshape(-1), Y.pow(2).sum().reshape(1)])
+    return float((stats - full).abs().max() / full.abs().max())
+
+
+def test_vfe_sufficient_statistics_shard_identity():
+    errs = _run(_vfe_stats_identity)
+    assert max(errs) < 1e-13
