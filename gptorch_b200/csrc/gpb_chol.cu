@@ -346,6 +346,114 @@ static int potrf_rec(CholCtx& c, int j0, int n) {
 
 static inline long npad128(long n) { return (n + NB - 1) / NB * NB; }
 
+// ---- look-ahead driver ---------------------------------------------------------------------------------
+// For large n the factorisation is organised in column panels of LA_PANEL columns.  The latency-bound work
+// (recursive factorisation of the panel's diagonal block, its TRSM) runs on a high-priority side stream
+// while the bulk trailing update of the PREVIOUS panel still occupies the chip on the caller's stream:
+//
+//   S0 (caller)  : ... 3a(p): update cols of panel p+1 | 3b(p): update everything right of panel p+1 | 3a(p+1) ...
+//   S1 (priority):                                     | potrf(diag p+1), trsm(panel p+1)            |
+//
+// 3b(p) only reads panel p and writes columns right of panel p+1, S1 only touches the columns of panel p+1.
+constexpr int LA_PANEL = 2048;
+constexpr int LA_MIN_N = 3 * LA_PANEL;
+
+struct AuxStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_update = nullptr, ev_fork = nullptr;
+  int device = -1;
+};
+
+static int get_aux(AuxStream** out) {
+  static AuxStream aux[64];
+  int dev = 0;
+  GPB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return GPB_ERR_UNSUPPORTED;
+  AuxStream& a = aux[dev];
+  if (a.stream == nullptr) {
+    int lo = 0, hi = 0;
+    GPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GPB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, hi));
+    GPB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev_panel, cudaEventDisableTiming));
+    GPB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev_update, cudaEventDisableTiming));
+    GPB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev_fork, cudaEventDisableTiming));
+    a.device = dev;
+  }
+  *out = &a;
+  return GPB_OK;
+}
+
+static int syrk_update(CholCtx& c, int r0, int m, int k0, int k) {
+  // A[r0:r0+m, r0:r0+m] (lower tiles) -= P P^T with P = A[r0:r0+m, k0:k0+k]
+  GemmArgs g;
+  g.M = m; g.N = m; g.K = k;
+  g.alpha = -1.0; g.beta = 1.0;
+  g.C = c.A + static_cast<long>(r0) * c.lda + r0;
+  g.ldc = c.lda;
+  g.ax = k0; g.ay = r0;
+  g.bx = k0; g.by = r0;
+  g.flags = GF_LOWER_TILES;
+  return gemm_launch(GEMM_NT, c.mapA128, c.mapA128, g, c.stream);
+}
+
+static int potrf_lookahead(CholCtx& c) {
+  AuxStream* aux = nullptr;
+  int rc = get_aux(&aux);
+  if (rc) return rc;
+  const cudaStream_t s0 = c.stream, s1 = aux->stream;
+  const int n = c.n, w = LA_PANEL;
+  GPB_CUDA_CHECK(cudaEventRecord(aux->ev_fork, s0));
+  GPB_CUDA_CHECK(cudaStreamWaitEvent(s1, aux->ev_fork, 0));
+  // panel 0
+  c.stream = s1;
+  rc = potrf_rec(c, 0, w);
+  if (rc) return rc;
+  rc = trsm_right_rec(c, w, n - w, 0, w);
+  if (rc) return rc;
+  GPB_CUDA_CHECK(cudaEventRecord(aux->ev_panel, s1));
+  for (int c0 = 0; c0 + w < n; c0 += w) {
+    const int c1 = c0 + w;
+    const int w1 = std::min(w, n - c1);
+    const int c2 = c1 + w1;
+    GPB_CUDA_CHECK(cudaStreamWaitEvent(s0, aux->ev_panel, 0));
+    // 3a: bring the columns of the next panel up to date
+    c.stream = s0;
+    rc = syrk_update(c, c1, w1, c0, w);
+    if (rc) return rc;
+    if (c2 < n) {
+      GemmArgs g;
+      g.M = n - c2; g.N = w1; g.K = w;
+      g.alpha = -1.0; g.beta = 1.0;
+      g.C = c.A + static_cast<long>(c2) * c.lda + c1;
+      g.ldc = c.lda;
+      g.ax = c0; g.ay = c2;
+      g.bx = c0; g.by = c1;
+      rc = gemm_launch(GEMM_NT, c.mapA128, c.mapA128, g, s0);
+      if (rc) return rc;
+    }
+    GPB_CUDA_CHECK(cudaEventRecord(aux->ev_update, s0));
+    // side stream: factor the next panel while 3b runs
+    GPB_CUDA_CHECK(cudaStreamWaitEvent(s1, aux->ev_update, 0));
+    c.stream = s1;
+    rc = potrf_rec(c, c1, w1);
+    if (rc) return rc;
+    if (c2 < n) {
+      rc = trsm_right_rec(c, c2, n - c2, c1, w1);
+      if (rc) return rc;
+    }
+    GPB_CUDA_CHECK(cudaEventRecord(aux->ev_panel, s1));
+    // 3b: the rest of the trailing matrix
+    c.stream = s0;
+    if (c2 < n) {
+      rc = syrk_update(c, c2, n - c2, c0, w);
+      if (rc) return rc;
+    }
+  }
+  GPB_CUDA_CHECK(cudaStreamWaitEvent(s0, aux->ev_panel, 0));
+  c.stream = s0;
+  return GPB_OK;
+}
+
 int potrf_lower(double* A, int n, long lda, double* dinv, int* info, cudaStream_t stream) {
   if (n <= 0) return GPB_OK;
   if (!A || !dinv || !info || lda < n) return GPB_ERR_BADARG;
@@ -355,6 +463,7 @@ int potrf_lower(double* A, int n, long lda, double* dinv, int* info, cudaStream_
   if (rc) return rc;
   rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 32);
   if (rc) return rc;
+  if (n >= LA_MIN_N) return potrf_lookahead(c);
   return potrf_rec(c, 0, n);
 }
 

@@ -84,6 +84,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
 }
+// Same instruction, but ordered with respect to the other volatile asm statements of the kernel (shared-memory
+// fragment loads, mbarrier arrives).  The TMA-ring GEMM must not let the compiler sink the MMAs that consume the
+// last fragments of a stage below the "stage empty" arrive: an MMA issues only once its operand loads have
+// returned, so MMA-before-arrive is what guarantees that no LDS of the stage is still in flight when the
+// producer is allowed to overwrite it.
+__device__ __forceinline__ void dmma884_ordered(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
 __device__ __forceinline__ double ld_shared_f64(uint32_t addr) {
   double v;

@@ -50,6 +50,7 @@ struct GemmKParams {
   int ax, ay, bx, by, dax, day, dbx, dby;
   unsigned flags;
   int tiles_m, tiles_n;
+  unsigned zero;   // always 0 at run time; opaque to the compiler (see the stage-release dependency in the main loop)
 };
 
 // Swizzled byte offset inside a "row-tile" (rows of 16 doubles = 128 B, SWIZZLE_128B): element (row, col).
@@ -109,15 +110,29 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   if (warp == Cfg::CONSUMER_WARPS) {
     // =============================== TMA producer ==============================================
+    // The whole warp walks the k-chunks in lock step; lane 0 arms the barrier and issues the TMA loads.  During
+    // the last PREFETCH_AHEAD chunks all 32 lanes also pull the C tile into L2 (beta != 0), a few 64-byte
+    // segments per chunk, so the epilogue's read-modify-write of C does not pay DRAM latency.
+    constexpr int PREFETCH_AHEAD = 24;
+    constexpr int SEG = BN / 8;                 // 64-byte segments per tile row
+    constexpr int TOTAL_SEG = BM * SEG;
+    const int pit = (p.beta != 0.0) ? max(nk - PREFETCH_AHEAD, 0) : nk;
+    const int seg_per_it = nk > pit ? (TOTAL_SEG + (nk - pit) - 1) / (nk - pit) : 0;
+    const bool diag_ws = (p.flags & GF_DIAG_TO_WS) && (m0 / NB) == (n0 / NB);
+    const double* Cp = diag_ws ? p.Cdiag : p.C + static_cast<long>(bz) * p.c_batch;
+    const long ldp = diag_ws ? p.ldd : p.ldc;
+    const int shift = diag_ws ? (n0 / NB) * NB : 0;
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapB);
-      const int ax = p.ax + bz * p.dax, ay = p.ay + bz * p.day;
-      const int bx = p.bx + bz * p.dbx, by = p.by + bz * p.dby;
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+    }
+    const int ax = p.ax + bz * p.dax, ay = p.ay + bz * p.day;
+    const int bx = p.bx + bz * p.dbx, by = p.by + bz * p.dby;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (lane == 0) {
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         uint8_t* a_dst = smem_al + s * STAGE_BYTES;
         uint8_t* b_dst = a_dst + A_TILE_BYTES;
@@ -139,6 +154,16 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int j = 0; j < BN / 16; ++j) tma_load_2d(b_dst + j * 2048, &mapB, bx + n0 + 16 * j, by + k, &full_bar[s]);
         }
       }
+      if (it >= pit) {
+        const int first = (it - pit) * seg_per_it;
+        for (int q = lane; q < seg_per_it; q += 32) {
+          const int idx = first + q;
+          const int row = m0 + idx / SEG, col = n0 + (idx % SEG) * 8;
+          if (idx < TOTAL_SEG && row < p.M && col < p.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp + static_cast<long>(row) * ldp - shift + col));
+        }
+      }
+      __syncwarp();
     }
     return;
   }
@@ -153,30 +178,42 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // Per-lane fragment offsets (bytes, relative to the A / B tile of a stage) for the 4 k4-steps.
-  //  K-contiguous operand tile [row][16 k]:   element (row, kcol) with kcol = 2s + (kk&1) + 8(kk>>1)
-  //  MN-contiguous operand tile [16 k][16 x] x (B?/16) sub-boxes: element (krow, x) with
-  //     krow = 2kk + (s&1) + 8(s>>1)  (TN: both operands)   or   krow = kcol above (NN: B operand).
-  uint32_t a_off[4], b_off[4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const uint32_t kcol_nt = 2 * s + (kk & 1) + 8 * (kk >> 1);
-    const uint32_t krow_tn = 2 * kk + (s & 1) + 8 * (s >> 1);
+  // Per-lane fragment offsets (bytes, relative to the A / B tile of a stage).  For k4-step s (0..3):
+  //  K-contiguous tile [row][16 k]: element (row, kcol), kcol = 2s + (kk&1) + 8(kk>>1): chunk = s + 4(kk>>1), so
+  //     off(s) = off(0) ^ (s << 4)                       (the XOR swizzle makes the step a bit flip)
+  //  MN-contiguous tile [16 k][16 x] per sub-box: element (krow, x) with
+  //     TN (both operands): krow = 2kk + (s&1) + 8(s>>1):  off(s) = (off(0) ^ ((s&1) << 4)) + (s&1)*128 + (s>>1)*1024
+  //     NN (B operand):     krow = kcol above:             off(s) = (off(0) ^ ((s&1) << 5)) + (s&1)*256 ... (see kn_off)
+  // Only the s = 0 offsets live in registers; the per-step part is an immediate.
+  uint32_t a_off0, b_off0;
+  {
+    const uint32_t kcol0 = (kk & 1) + 8 * (kk >> 1);
+    const uint32_t krow0 = 2 * kk;
     if (MODE == GEMM_TN) {
       const uint32_t ml = wm * WM + r;  // + 8i added below (i even/odd changes the sub-box column half)
-      a_off[s] = (ml >> 4) * 2048u + swz(krow_tn, ml & 15u);
+      a_off0 = (ml >> 4) * 2048u + swz(krow0, ml & 15u);
       const uint32_t nl = wn * WN + r;
-      b_off[s] = (nl >> 4) * 2048u + swz(krow_tn, nl & 15u);
+      b_off0 = (nl >> 4) * 2048u + swz(krow0, nl & 15u);
     } else {
-      a_off[s] = swz(wm * WM + r, kcol_nt);
+      a_off0 = swz(wm * WM + r, kcol0);
       if (MODE == GEMM_NT) {
-        b_off[s] = swz(wn * WN + r, kcol_nt);
+        b_off0 = swz(wn * WN + r, kcol0);
       } else {
         const uint32_t nl = wn * WN + r;
-        b_off[s] = (nl >> 4) * 2048u + swz(kcol_nt, nl & 15u);
+        b_off0 = (nl >> 4) * 2048u + swz(kcol0, nl & 15u);
       }
     }
   }
+  // step offsets as functions of the compile-time step index
+  auto kc_off = [](uint32_t off0, int s) -> uint32_t { return off0 ^ (static_cast<uint32_t>(s) << 4); };
+  auto tn_off = [](uint32_t off0, int s) -> uint32_t {
+    return (off0 ^ (static_cast<uint32_t>(s & 1) << 4)) + static_cast<uint32_t>(s & 1) * 128u + static_cast<uint32_t>(s >> 1) * 1024u;
+  };
+  // NN B operand: krow = 2s + (kk&1) + 8(kk>>1): row offset +256 s bytes; (krow & 7) = (2s + (kk&1)) & 7 flips chunk
+  // bits 1-2 by s (2s < 8): chunk ^= 2s  -> byte offset bits 5-6 ^= s.
+  auto kn_off = [](uint32_t off0, int s) -> uint32_t {
+    return (off0 ^ (static_cast<uint32_t>(s) << 5)) + static_cast<uint32_t>(s) * 256u;
+  };
 
   for (int it = 0; it < nk; ++it) {
     const int s = it % STAGES;
@@ -184,6 +221,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     mbar_wait(&full_bar[s], ph);
     const uint32_t a_base = smem_base + s * STAGE_BYTES;
     const uint32_t b_base = a_base + A_TILE_BYTES;
+    uint32_t dep = 0;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       double a[MI], b[NI];
@@ -192,10 +230,10 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         uint32_t off;
         if (MODE == GEMM_TN) {
           // rows 8i of the warp tile: i odd -> columns 8..15 of the sub-box (chunk index + 4), i>>1 -> next sub-box
-          off = a_off[ks] + (i >> 1) * 2048u;
+          off = tn_off(a_off0, ks) + (i >> 1) * 2048u;
           if (i & 1) off ^= 64u;  // (x>>1) + 4 under the XOR swizzle == flip bit 6 of the byte offset
         } else {
-          off = a_off[ks] + i * 1024u;  // 8 rows x 128 B; row & 7 unchanged
+          off = kc_off(a_off0, ks) + i * 1024u;  // 8 rows x 128 B; row & 7 unchanged
         }
         a[i] = ld_shared_f64(a_base + off);
       }
@@ -203,20 +241,31 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int j = 0; j < NI; ++j) {
         uint32_t off;
         if (MODE == GEMM_NT) {
-          off = b_off[ks] + j * 1024u;
+          off = kc_off(b_off0, ks) + j * 1024u;
         } else {
-          off = b_off[ks] + (j >> 1) * 2048u;
+          off = (MODE == GEMM_TN ? tn_off(b_off0, ks) : kn_off(b_off0, ks)) + (j >> 1) * 2048u;
           if (j & 1) off ^= 64u;
         }
         b[j] = ld_shared_f64(b_base + off);
+      }
+      if (ks == 3) {
+        // Every fragment register of the last k-step feeds `dep`: the stage-release below cannot issue before
+        // these (in-order) shared-memory loads have returned.
+#pragma unroll
+        for (int i = 0; i < MI; ++i) dep |= static_cast<uint32_t>(__double2hiint(a[i]));
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dep |= static_cast<uint32_t>(__double2hiint(b[j]));
       }
 #pragma unroll
       for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    // Release the stage to the TMA producer.  The arrive must not overtake any LDS of this stage (the compiler
+    // and ptxas are free to sink the MMAs below it), so its address carries a data dependency on the loaded
+    // fragments of ALL lanes: warp-wide OR, masked with a run-time zero.
+    dep = __reduce_or_sync(0xffffffffu, dep) & p.zero;
+    if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(&empty_bar[s]) + dep));
   }
 
   // ---------------------------------- epilogue ---------------------------------------------------
@@ -229,6 +278,48 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     col_shift = (n0 / NB) * NB;
   }
   const double alpha = p.alpha, beta = p.beta;
+  const int col_base = n0 + wn * WN + 2 * kk;
+  const bool full_cols = (n0 + wn * WN + WN) <= p.N;   // every column pair of this warp tile is in range
+  if (full_cols) {
+    // Fast path.  The C tile was prefetched into L2 by the producer warp's spare lanes; it is read in batches
+    // of EB row groups (EB x NI double2 loads in flight per thread) before anything is stored, so the memory
+    // latency is paid once per batch instead of once per element pair.
+    constexpr int EB = (MI * NI > 16) ? 1 : 2;   // row groups per batch (register budget: 168 with 9 warps)
+#pragma unroll
+    for (int i0 = 0; i0 < MI; i0 += EB) {
+      double cx[EB][NI], cy[EB][NI];
+#pragma unroll
+      for (int ii = 0; ii < EB; ++ii) {
+        const int row = m0 + wm * WM + 8 * (i0 + ii) + r;
+        const double* crow = Cb + static_cast<long>(row) * ldc - col_shift + col_base;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          cx[ii][j] = 0.0;
+          cy[ii][j] = 0.0;
+          if (beta != 0.0 && row < p.M) {
+            const double2 t = *reinterpret_cast<const double2*>(crow + 8 * j);
+            cx[ii][j] = t.x;
+            cy[ii][j] = t.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < EB; ++ii) {
+        const int row = m0 + wm * WM + 8 * (i0 + ii) + r;
+        double* crow = Cb + static_cast<long>(row) * ldc - col_shift + col_base;
+        if (row < p.M) {
+#pragma unroll
+          for (int j = 0; j < NI; ++j) {
+            double2 v;
+            v.x = alpha * acc[i0 + ii][j][0] + beta * cx[ii][j];
+            v.y = alpha * acc[i0 + ii][j][1] + beta * cy[ii][j];
+            *reinterpret_cast<double2*>(crow + 8 * j) = v;
+          }
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
     const int row = m0 + wm * WM + 8 * i + r;
@@ -312,6 +403,7 @@ int gemm_launch(GemmMode mode, const CUtensorMap& mapA, const CUtensorMap& mapB,
   kp.dax = a.dax; kp.day = a.day; kp.dbx = a.dbx; kp.dby = a.dby;
   kp.flags = a.flags;
   kp.tiles_m = kp.tiles_n = 0;
+  kp.zero = 0u;
   if ((a.flags & GF_DIAG_TO_WS) && (a.Cdiag == nullptr || (a.ldd & 1))) return GPB_ERR_BADARG;
   switch (mode) {
     case GEMM_NT: return launch_mode<GEMM_NT>(mapA, mapB, kp, a, stream);

@@ -56,7 +56,7 @@ Kr = ref_K(0, X, None, ell, s2) + 0.01 * torch.eye(700, dtype=torch.float64, dev
 report("kern_fwd lower+noise", rel(torch.tril(Kl), torch.tril(Kr)), 1e-13)
 
 # ---- potrf / trsv / logdet / potri
-for n in (5, 100, 128, 129, 300, 1000, 2048, 4100):
+for n in (5, 100, 128, 129, 300, 1000, 2048, 4100, 6400, 8300):
     X = torch.rand(n, 8, dtype=torch.float64, device=dev)
     K = ref_K(0, X, None, torch.ones(8, dtype=torch.float64, device=dev), 1.0) + 0.01 * torch.eye(n, dtype=torch.float64, device=dev)
     Lref = torch.linalg.cholesky(K)
