@@ -173,6 +173,34 @@ def fp64_peak_live():
     return 2.0 * n ** 3 / best / 1e9
 
 
+PROBE_M, PROBE_K = 16384, 2048
+PROBE_TRAFFIC_BYTES = 5.50e9   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_syrk_16384x2048.txt
+
+
+def dominant_launch_probe():
+    """One launch shape of the dominant kernel timed on its own with CUDA events: the SYRK trailing update
+    (lower tiles) m = n = 16384, k = 2048 -- the shape profiled with ncu --set full in profiles/."""
+    from gptorch_b200 import _native as nv
+    A = torch.randn(PROBE_M, PROBE_K, dtype=torch.float64, device="cuda")
+    C = torch.randn(PROBE_M, PROBE_M, dtype=torch.float64, device="cuda")
+    run = lambda: nv.gemm(nv.GEMM_NT, A, A, alpha=-1.0, beta=1.0, C=C, lower_only=True)  # noqa: E731
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    tiles = (PROBE_M // 128) * (PROBE_M // 128 + 1) // 2
+    flop = 2.0 * tiles * 128 * 128 * PROBE_K
+    del A, C
+    torch.cuda.empty_cache()
+    return {"shape": "syrk lower m=n=%d k=%d (%d tiles of 128x128; C is 2.1 GB > L2)" % (PROBE_M, PROBE_K, tiles),
+            "ms": ms, "flop": flop, "tflops": flop / ms / 1e9}
+
+
 def build_model(n, device):
     from oracle import gp_oracle as O   # input generator only (shared with the oracle so the loss pins apply)
     from gptorch_b200 import kernels, likelihoods
@@ -262,6 +290,7 @@ def run_ours(args, rank, world, local_rank):
     n3 = float(n) ** 3
     chol_tflops = n3 / 3.0 / potrf_ms / 1e9 if potrf_ms else None
     o3_tflops = n3 / (potrf_ms + potri_ms) / 1e9 if (potrf_ms + potri_ms) else None
+    probe = dominant_launch_probe()
     # pins from the reference for the sizes the oracle could run
     pins = {1024: -606.3903292756472, 2048: -1420.2752146205817, 4096: -2680.7933915936683,
             8192: -6511.334472842767, 16384: -13224.865836863326}
@@ -276,12 +305,17 @@ def run_ours(args, rank, world, local_rank):
         "chol_tflops": chol_tflops,
         "phases_ms_per_step": {k: v / steps for k, v in sorted(phases.items())},
         "roofline": {"bound": "tensor", "achieved": o3_tflops, "peak": peak, "unit": "TFLOP/s",
-                     "frac": (o3_tflops / peak) if o3_tflops else None, "traffic": None,
-                     "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4 + TMA) inside gpb_potrf_lower + gpb_potri_lower",
-                     "algorithmic": "N^3 flop per eval (potrf N^3/3 + potri 2N^3/3) over the CUDA-event time of those two phases",
+                     "frac": (o3_tflops / peak) if o3_tflops else None,
+                     "traffic": PROBE_TRAFFIC_BYTES,
+                     "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4 fed by TMA) -- > 95 % of gpb_potrf_lower + gpb_potri_lower",
+                     "algorithmic": "achieved = N^3 flop per eval (potrf N^3/3 + potri 2N^3/3) / CUDA-event time of those two "
+                                    "phases inside the timed steps (all their launches, including the latency-bound ones)",
                      "peak_source": "measured live: cuBLAS DGEMM 8192^3 best of 5 (MEASURED_PEAKS.json has no FP64 entry); "
                                     "DMMA issue-rate probe on this pool: %.1f TFLOP/s" % FP64_DMMA_PROBE_TFLOPS,
-                     "chol_frac": (chol_tflops / peak) if chol_tflops else None},
+                     "chol_frac": (chol_tflops / peak) if chol_tflops else None,
+                     "launch_probe": probe,
+                     "traffic_note": "dram__bytes_read+write of ONE launch of the probe shape from ncu --set full "
+                                     "(profiles/r01_ncu_syrk_16384x2048.txt); algorithmic bytes of that launch: 2.43e9"},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -222,6 +222,7 @@ class GemmFn(Function):
 # fused GPR log marginal likelihood
 # ------------------------------------------------------------------------------------------------------
 JITTER_TRIES = 10  # gptorch/functions.py:21
+VFE_SPLITS = 16    # k-slices of the streamed Gram products (fills the GPU when M x M has few tiles)
 
 
 class GPRLogLikFn(Function):
@@ -303,18 +304,21 @@ class VfeStatsFn(Function):
         Lc = nv._gemm_operand(L)
         dinv = _dinv_of(L)
         n, m, dy = X.shape[0], Z.shape[0], Y.shape[1]
-        AA, ldaa = nv._aligned_empty(m, m, X.device)
-        AA.zero_()
-        AY, _ = nv._aligned_empty(m, dy, X.device)
-        AY.zero_()
+        # The M x M Gram output has only (M/128)^2/2 tiles, far fewer than the GPU has SMs, so the long k = rows
+        # dimension is cut into VFE_SPLITS slices that accumulate into separate slots, summed at the end.
+        kper = VfeStatsFn._k_per_split(min(chunk, n))
+        ldm = m + (m & 1)
+        AA3 = torch.zeros((VFE_SPLITS, m, ldm), dtype=torch.float64, device=X.device)
+        ldy = dy + (dy & 1)
+        AY3 = torch.zeros((VFE_SPLITS, m, ldy), dtype=torch.float64, device=X.device)
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
             At, ldat = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, Lc, dinv)
-            nv.gemm(nv.GEMM_TN, At, At, beta=1.0, C=AA[:, :m], lower_only=True)
-            nv.gemm(nv.GEMM_TN, At, Y[s:e], beta=1.0, C=AY[:, :dy])
-        AAf = AA[:, :m]
+            nv.gemm_splitk(nv.GEMM_TN, At, At, kper, AA3, beta=1.0, lower_only=True)
+            nv.gemm_splitk(nv.GEMM_TN, At, Y[s:e], kper, AY3, beta=1.0)
+        AAf = AA3.sum(0)[:, :m]
         AAf = torch.tril(AAf) + torch.tril(AAf, -1).t()
-        AYf = AY[:, :dy].contiguous()
+        AYf = AY3.sum(0)[:, :dy].contiguous()
         # sum_i k(x_i, x_i) = n * sigma2 for a stationary kernel (gptorch/kernels.py:174-179); sum Y^2
         scal = torch.stack([sigma2.reshape(()) * float(n), nv.logdet_sumsq(None, Y)[1]])
         if group is not None:
@@ -324,6 +328,11 @@ class VfeStatsFn(Function):
         ctx.kind, ctx.chunk, ctx.group, ctx.n_local = kind, chunk, group, n
         ctx.save_for_backward(X, Y, Z, ell, sigma2, Lc, dinv, AAf, AYf)
         return AAf, AYf, scal[0], scal[1]
+
+    @staticmethod
+    def _k_per_split(rows):
+        per = (rows + VFE_SPLITS - 1) // VFE_SPLITS
+        return max(16, (per + 15) // 16 * 16)
 
     @staticmethod
     def _panel(kind, Xc, Z, ell, sigma2, L, dinv):

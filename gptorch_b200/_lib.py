@@ -50,6 +50,8 @@ SIGNATURES = {
     "gpb_logdet_sumsq": (c_int, [c_void_p, c_int, c_long, c_void_p, c_int, c_int, c_long, c_void_p, c_void_p]),
     "gpb_gemm": (c_int, [c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double,
                          c_void_p, c_long, c_int, c_void_p]),
+    "gpb_gemm_splitk": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double,
+                                c_void_p, c_long, c_long, c_int, c_void_p]),
     "gpb_gpr_grad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gpb_gpr_grad": (c_int, [c_int, c_void_p, c_int, c_long, c_int, c_void_p, c_int, c_void_p, c_void_p, c_long,
                              c_void_p, c_void_p, c_int, c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

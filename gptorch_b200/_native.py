@@ -279,6 +279,27 @@ def gemm(mode, A, B, alpha=1.0, beta=0.0, C=None, lower_only=False):
     return C
 
 
+def gemm_splitk(mode, A, B, k_per_split, C3, beta=1.0, alpha=1.0, lower_only=False):
+    """Split-K GEMM: slice s of the k range accumulates into C3[s] (C3: [splits, m, ld] with ld even)."""
+    A = _gemm_operand(A)
+    B = _gemm_operand(B)
+    if mode == GEMM_TN:
+        k, m = A.shape
+        n = B.shape[1]
+    elif mode == GEMM_NT:
+        m, k = A.shape
+        n = B.shape[0]
+    else:
+        m, k = A.shape
+        n = B.shape[1]
+    splits = (k + k_per_split - 1) // k_per_split
+    if C3.shape[0] < splits or C3.shape[1] != m or C3.shape[2] < n:
+        raise ValueError("gemm_splitk: C3 must be [>= %d, %d, >= %d]" % (splits, m, n))
+    call("gpb_gemm_splitk", mode, m, n, k, k_per_split, float(alpha), ptr(A), A.stride(0), ptr(B), B.stride(0),
+         float(beta), ptr(C3), C3.stride(1), C3.stride(0), 1 if lower_only else 0, stream_ptr())
+    return C3
+
+
 # ---------------------------------------------------------------------------------------------- fused GPR gradient
 def gpr_grad(kind, X, ell, sigma2, Kinv, ldk, kd, a):
     """Returns (g_ell, g_sigma2, g_noise): d loss / d (ell, sigma2, sigma_n^2) for the GPR loss."""

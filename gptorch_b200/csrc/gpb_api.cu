@@ -133,6 +133,33 @@ int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long 
   return gemm_launch(gm, mapA, mapB, g, S(stream));
 }
 
+int gpb_gemm_splitk(int mode, int m, int n, int k_total, int k_per_split, double alpha, const double* A, long lda,
+                    const double* B, long ldb, double beta, double* C, long ldc, long c_split_stride, int lower_only,
+                    void* stream) {
+  if (mode < 0 || mode > 2 || m <= 0 || n <= 0 || k_total <= 0 || k_per_split <= 0) return GPB_ERR_BADARG;
+  if (!A || !B || !C || (k_per_split % 16) != 0) return GPB_ERR_BADARG;
+  const GemmMode gm = static_cast<GemmMode>(mode);
+  const int splits = (k_total + k_per_split - 1) / k_per_split;
+  CUtensorMap mapA, mapB;
+  const long a_rows = gm == GEMM_TN ? k_total : m, a_cols = gm == GEMM_TN ? m : k_total;
+  const long b_rows = gm == GEMM_NT ? n : k_total, b_cols = gm == GEMM_NT ? k_total : n;
+  int rc = make_tmap_f64(&mapA, A, a_rows, a_cols, lda, gemm_box_rows_a(gm));
+  if (rc) return rc;
+  rc = make_tmap_f64(&mapB, B, b_rows, b_cols, ldb, gemm_box_rows_b(gm));
+  if (rc) return rc;
+  GemmArgs g;
+  g.M = m; g.N = n; g.K = k_per_split;
+  g.alpha = alpha; g.beta = beta;
+  g.C = C; g.ldc = ldc; g.c_batch = c_split_stride;
+  g.batch = splits;
+  // the k index is the row index for MN-contiguous operands and the column index for K-contiguous ones
+  if (gm == GEMM_TN) { g.day = k_per_split; g.dby = k_per_split; }
+  else if (gm == GEMM_NT) { g.dax = k_per_split; g.dbx = k_per_split; }
+  else { g.dax = k_per_split; g.dby = k_per_split; }
+  g.flags = lower_only ? GF_LOWER_TILES : 0u;
+  return gemm_launch(gm, mapA, mapB, g, S(stream));
+}
+
 size_t gpb_gpr_grad_workspace_bytes(int n, int D) { return gpr_grad_workspace_bytes(n, D); }
 int gpb_gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* ell, int ell_len,
                  const double* sigma2, const double* Kinv, long ldk, const double* kdiag_blocks, const double* a,

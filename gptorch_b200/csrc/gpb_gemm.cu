@@ -73,19 +73,51 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- tile coordinates -------------------------------------------------------------------------
+  // Tiles are visited in super-blocks of SUPER x SUPER tiles (about one wave of 148 CTAs): the CTAs that are
+  // resident together then share SUPER row panels and SUPER column panels, which stay in L2 instead of being
+  // re-fetched from HBM for every tile.  Super-block rows ascend, so LAUUM's heaviest tiles still go first.
   int tm, tn;
   {
-    const int t = blockIdx.x;
+    constexpr int SUPER = 12;
+    int t = blockIdx.x;
     if (p.flags & GF_LOWER_TILES) {
-      // row-major enumeration of the lower triangle: t = tm(tm+1)/2 + tn
-      int r = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-      while ((r + 1) * (r + 2) / 2 <= t) ++r;
-      while (r * (r + 1) / 2 > t) --r;
-      tm = r;
-      tn = t - r * (r + 1) / 2;
+      const int T = p.tiles_m;
+      int sm = 0, r0 = 0, h = min(SUPER, T);
+      for (;;) {
+        const int cnt = h * SUPER * sm + h * (h + 1) / 2;
+        if (t < cnt) break;
+        t -= cnt;
+        ++sm;
+        r0 += SUPER;
+        h = min(SUPER, T - r0);
+      }
+      const int off_diag = h * SUPER * sm;
+      if (t < off_diag) {
+        const int sn = t / (h * SUPER), q = t - sn * (h * SUPER);
+        tm = r0 + q / SUPER;
+        tn = sn * SUPER + q % SUPER;
+      } else {
+        const int q = t - off_diag;
+        int i = static_cast<int>((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= q) ++i;
+        while (i * (i + 1) / 2 > q) --i;
+        tm = r0 + i;
+        tn = r0 + (q - i * (i + 1) / 2);
+      }
     } else {
-      tm = t / p.tiles_n;
-      tn = t - tm * p.tiles_n;
+      const int Tn = p.tiles_n;
+      const int rows_per_super = SUPER * Tn;            // tiles in one full super row
+      const int sm = t / rows_per_super;
+      const int r0 = sm * SUPER;
+      const int h = min(SUPER, p.tiles_m - r0);
+      t -= sm * rows_per_super;
+      const int per_block = h * SUPER;                    // tiles in one full super-block of this super row
+      const int sn = t / per_block;
+      const int c0 = sn * SUPER;
+      const int w = min(SUPER, Tn - c0);
+      const int q = t - sn * per_block;
+      tm = r0 + q / w;
+      tn = c0 + q % w;
     }
   }
   const int m0 = tm * BM, n0 = tn * BN;

@@ -149,6 +149,14 @@ int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrow
 int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,
              double beta, double* C, long ldc, int lower_only, void* stream);
 
+/* Split-K form: the k range is cut into ceil(k_total / k_per_split) slices (k_per_split a multiple of 16) that run
+ * as independent CTAs; slice s accumulates into C + s * c_split_stride.  Used for the Gram products of the sparse
+ * models, whose M x M output has far fewer tiles than the GPU has SMs (A A^T over N >> M rows,
+ * gptorch/models/sparse_gpr.py:133); the caller sums the slices (deterministic, fixed order). */
+int gpb_gemm_splitk(int mode, int m, int n, int k_total, int k_per_split, double alpha, const double* A, long lda,
+                    const double* B, long ldb, double beta, double* C, long ldc, long c_split_stride, int lower_only,
+                    void* stream);
+
 /* ---- fused GPR gradient ------------------------------------------------------------------------------------
  * Given Kinv in the blocked form left by gpb_potri_lower and a = Ky^-1 (y - m) (n x dy, lda_a), reduce
  *    W = 1/2 (dy * Kinv - a a^T)            (dLoss/dKy; gptorch/models/gpr.py:47-67)
