@@ -222,6 +222,7 @@ class GemmFn(Function):
 # fused GPR log marginal likelihood
 # ------------------------------------------------------------------------------------------------------
 JITTER_TRIES = 10  # gptorch/functions.py:21
+VFE_PANEL_CACHE_BYTES = 48 << 30   # keep A^T panels for backward up to this size (B200: 180 GB HBM)
 VFE_SPLITS = 16    # k-slices of the streamed Gram products (fills the GPU when M x M has few tiles)
 
 
@@ -311,11 +312,18 @@ class VfeStatsFn(Function):
         AA3 = torch.zeros((VFE_SPLITS, m, ldm), dtype=torch.float64, device=X.device)
         ldy = dy + (dy & 1)
         AY3 = torch.zeros((VFE_SPLITS, m, ldy), dtype=torch.float64, device=X.device)
+        # Keep the solved panels A^T for the backward pass when they fit the budget (N*M*8 bytes); otherwise the
+        # backward pass re-streams them from X (one more covariance build + solve per chunk).
+        keep = any(ctx.needs_input_grad) and n * ldm * 8 <= VFE_PANEL_CACHE_BYTES
+        cache = []
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
             At, ldat = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, Lc, dinv)
-            nv.gemm_splitk(nv.GEMM_TN, At, At, kper, AA3, beta=1.0, lower_only=True)
-            nv.gemm_splitk(nv.GEMM_TN, At, Y[s:e], kper, AY3, beta=1.0)
+            if keep:
+                cache.append(At)
+            with nv.phase("vfe_gram"):
+                nv.gemm_splitk(nv.GEMM_TN, At, At, kper, AA3, beta=1.0, lower_only=True)
+                nv.gemm_splitk(nv.GEMM_TN, At, Y[s:e], kper, AY3, beta=1.0)
         AAf = AA3.sum(0)[:, :m]
         AAf = torch.tril(AAf) + torch.tril(AAf, -1).t()
         AYf = AY3.sum(0)[:, :dy].contiguous()
@@ -326,6 +334,7 @@ class VfeStatsFn(Function):
             torch.distributed.all_reduce(AYf, group=group)
             torch.distributed.all_reduce(scal, group=group)
         ctx.kind, ctx.chunk, ctx.group, ctx.n_local = kind, chunk, group, n
+        ctx.panels = cache if keep else None
         ctx.save_for_backward(X, Y, Z, ell, sigma2, Lc, dinv, AAf, AYf)
         return AAf, AYf, scal[0], scal[1]
 
@@ -336,10 +345,12 @@ class VfeStatsFn(Function):
 
     @staticmethod
     def _panel(kind, Xc, Z, ell, sigma2, L, dinv):
-        Kfu = nv.kern_fwd(kind, Xc, Z, ell, sigma2)
+        with nv.phase("vfe_kern_fwd"):
+            Kfu = nv.kern_fwd(kind, Xc, Z, ell, sigma2)
         ld = Kfu.stride(0)
-        nv.call("gpb_trsm_right_lt", nv.ptr(L), L.shape[0], L.stride(0), nv.ptr(dinv), nv.ptr(Kfu), Kfu.shape[0], ld,
-                nv.stream_ptr())
+        with nv.phase("vfe_trsm"):
+            nv.call("gpb_trsm_right_lt", nv.ptr(L), L.shape[0], L.stride(0), nv.ptr(dinv), nv.ptr(Kfu), Kfu.shape[0], ld,
+                    nv.stream_ptr())
         return Kfu, ld
 
     @staticmethod
@@ -356,12 +367,19 @@ class VfeStatsFn(Function):
         g_ell = torch.zeros_like(ell.reshape(-1))
         g_s2 = torch.zeros(1, dtype=torch.float64, device=X.device)
         gZ = torch.zeros_like(Z)
-        for s in range(0, n, chunk):
+        panels, ctx.panels = ctx.panels, None
+        for ci, s in enumerate(range(0, n, chunk)):
             e = min(n, s + chunk)
-            At, _ = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, L, dinv)
-            G = nv.gemm(nv.GEMM_NN, At, R)
-            nv.gemm(nv.GEMM_NT, Y[s:e], w, beta=1.0, C=G)
-            ge, gs, gz = nv.kern_bwd(kind, X[s:e], Z, ell, sigma2, G, True)
+            if panels is not None:
+                At = panels[ci]
+                panels[ci] = None
+            else:
+                At, _ = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, L, dinv)
+            with nv.phase("vfe_bwd_gemm"):
+                G = nv.gemm(nv.GEMM_NN, At, R)
+                nv.gemm(nv.GEMM_NT, Y[s:e], w, beta=1.0, C=G)
+            with nv.phase("vfe_kern_bwd"):
+                ge, gs, gz = nv.kern_bwd(kind, X[s:e], Z, ell, sigma2, G, True)
             g_ell += ge
             g_s2 += gs
             gZ += gz

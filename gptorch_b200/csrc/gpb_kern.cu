@@ -60,7 +60,9 @@ __device__ __forceinline__ void kern_base_fac(int kind, double r2, double& kbase
 // ================================================================================================
 // forward
 // ================================================================================================
-constexpr int KF_TILE = 128;
+constexpr int KF_TM = 64;     // tile rows  (2 warps x 32)
+constexpr int KF_TN = 128;    // tile cols  (4 warps x 32)
+constexpr int KF_MI = 4, KF_NI = 4;   // 8x8 DMMA fragments per warp tile (32 x 32): 32 accumulators per thread
 constexpr int KF_DC = 16;    // feature chunk staged per pass
 constexpr int KF_LD = 20;    // padded row stride (doubles): 20 mod 16 == 4 -> conflict-free DMMA fragment loads
 constexpr int KF_THREADS = 256;
@@ -79,38 +81,43 @@ struct KfwdParams {
   int tiles_n;
 };
 
-__global__ void __launch_bounds__(KF_THREADS, 1) kern_fwd_kernel(const KfwdParams p) {
-  __shared__ double As[KF_TILE * KF_LD];
-  __shared__ double Bs[KF_TILE * KF_LD];
-  __shared__ double na[KF_TILE], nbv[KF_TILE];
+// 64 x 128 tile per CTA, 8 warps (2 x 4) of 32 x 32: 32 fp64 accumulators per thread keeps the kernel at two CTAs
+// (16 warps) per SM, which is what hides the latency of the exp() chains in the epilogue.
+__global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParams p) {
+  __shared__ double As[KF_TM * KF_LD];
+  __shared__ double Bs[KF_TN * KF_LD];
+  __shared__ double na[KF_TM], nbv[KF_TN];
   __shared__ double scale[KF_DC];
 
   int tm, tn;
   {
     const int t = blockIdx.x;
     if (p.lower) {
-      int r = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-      while ((r + 1) * (r + 2) / 2 <= t) ++r;
-      while (r * (r + 1) / 2 > t) --r;
-      tm = r;
-      tn = t - r * (r + 1) / 2;
+      // lower triangle in units of 128-column blocks: tile row tm (64 rows) needs column tiles 0 .. tm/2
+      // enumerate pairs of tile rows: rows (2q, 2q+1) each have q+1 column tiles
+      int q = static_cast<int>((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
+      while ((q + 1) * (q + 2) <= t) ++q;
+      while (q * (q + 1) > t) --q;
+      const int rem = t - q * (q + 1);      // 0 .. 2(q+1)-1
+      tm = 2 * q + rem / (q + 1);
+      tn = rem % (q + 1);
     } else {
       tm = t / p.tiles_n;
       tn = t - tm * p.tiles_n;
     }
   }
-  const int m0 = tm * KF_TILE, n0 = tn * KF_TILE;
+  const int m0 = tm * KF_TM, n0 = tn * KF_TN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 1, wn = warp >> 1;
   const int r = lane >> 2, kk = lane & 3;
   const bool linear = p.kind == KERN_LINEAR;
 
-  double acc[8][4][2];
+  double acc[KF_MI][KF_NI][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < KF_MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  double my_na = 0.0, my_nb = 0.0;  // thread t < 128 accumulates the squared norm of row t of each operand
+    for (int j = 0; j < KF_NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double my_n = 0.0;  // thread t < 64: squared norm of A row t; 64 <= t < 192: of B row t - 64
 
   for (int d0 = 0; d0 < p.D; d0 += KF_DC) {
     __syncthreads();
@@ -121,62 +128,59 @@ __global__ void __launch_bounds__(KF_THREADS, 1) kern_fwd_kernel(const KfwdParam
       scale[tid] = s;
     }
     __syncthreads();
-    for (int idx = tid; idx < KF_TILE * KF_DC; idx += KF_THREADS) {
+    for (int idx = tid; idx < (KF_TM + KF_TN) * KF_DC; idx += KF_THREADS) {
       const int row = idx >> 4, k = idx & 15;
       const int d = d0 + k;
-      double va = 0.0, vb = 0.0;
-      if (d < p.D) {
-        if (m0 + row < p.n1) {
+      double v = 0.0;
+      if (row < KF_TM) {
+        if (d < p.D && m0 + row < p.n1) {
           const double x = p.X[static_cast<long>(m0 + row) * p.ldx + d];
-          va = linear ? x * scale[k] : x / scale[k];
+          v = linear ? x * scale[k] : x / scale[k];
         }
-        if (n0 + row < p.n2) {
-          const double x = p.X2[static_cast<long>(n0 + row) * p.ldx2 + d];
-          vb = linear ? x : x / scale[k];
+        As[row * KF_LD + k] = v;
+      } else {
+        const int rb = row - KF_TM;
+        if (d < p.D && n0 + rb < p.n2) {
+          const double x = p.X2[static_cast<long>(n0 + rb) * p.ldx2 + d];
+          v = linear ? x : x / scale[k];
         }
+        Bs[rb * KF_LD + k] = v;
       }
-      As[row * KF_LD + k] = va;
-      Bs[row * KF_LD + k] = vb;
     }
     __syncthreads();
-    if (tid < KF_TILE) {
+    if (tid < KF_TM + KF_TN) {
+      const double* src = tid < KF_TM ? &As[tid * KF_LD] : &Bs[(tid - KF_TM) * KF_LD];
 #pragma unroll
-      for (int k = 0; k < KF_DC; ++k) {
-        const double a = As[tid * KF_LD + k], b = Bs[tid * KF_LD + k];
-        my_na += a * a;
-        my_nb += b * b;
-      }
+      for (int k = 0; k < KF_DC; ++k) my_n += src[k] * src[k];
     }
+    const int ksteps = min(KF_DC, p.D - d0 + 3) / 4;   // skip k4-steps that are all padding
+    for (int ks = 0; ks < ksteps; ++ks) {
+      double a[KF_MI], b[KF_NI];
 #pragma unroll
-    for (int ks = 0; ks < KF_DC / 4; ++ks) {
-      double a[8], b[4];
+      for (int i = 0; i < KF_MI; ++i) a[i] = As[(wm * 32 + 8 * i + r) * KF_LD + ks * 4 + kk];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = As[(wm * 64 + 8 * i + r) * KF_LD + ks * 4 + kk];
+      for (int j = 0; j < KF_NI; ++j) b[j] = Bs[(wn * 32 + 8 * j + r) * KF_LD + ks * 4 + kk];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[(wn * 32 + 8 * j + r) * KF_LD + ks * 4 + kk];
+      for (int i = 0; i < KF_MI; ++i)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < KF_NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
-  if (tid < KF_TILE) {
-    na[tid] = my_na;
-    nbv[tid] = my_nb;
-  }
+  if (tid < KF_TM) na[tid] = my_n;
+  else if (tid < KF_TM + KF_TN) nbv[tid - KF_TM] = my_n;
   __syncthreads();
 
   const double sig2 = linear ? 1.0 : *p.sigma2;
   const double noise = (p.symmetric && p.noise) ? *p.noise : 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int lr = wm * 64 + 8 * i + r;
+  for (int i = 0; i < KF_MI; ++i) {
+    const int lr = wm * 32 + 8 * i + r;
     const int row = m0 + lr;
     if (row >= p.n1) continue;
     const double nrow = na[lr];
     double* krow = p.K + static_cast<long>(row) * p.ldk;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < KF_NI; ++j) {
       const int lc = wn * 32 + 8 * j + 2 * kk;
       const int col = n0 + lc;
       double v[2];
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(KF_THREADS, 1) kern_fwd_kernel(const KfwdParam
         if (p.symmetric && row == col + e) v[e] += noise;
       }
       if (col + 1 < p.n2 && ((p.ldk & 1) == 0)) {
-        *reinterpret_cast<double2*>(krow + col) = make_double2(v[0], v[1]);
+        __stcs(reinterpret_cast<double2*>(krow + col), make_double2(v[0], v[1]));
       } else {
         if (col < p.n2) krow[col] = v[0];
         if (col + 1 < p.n2) krow[col + 1] = v[1];
@@ -225,9 +229,14 @@ int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int 
   p.lower = (fill == 1);
   if (p.lower && !p.symmetric) return GPB_ERR_BADARG;
   p.K = K; p.ldk = ldk;
-  const int tiles_m = (n1 + KF_TILE - 1) / KF_TILE;
-  p.tiles_n = (p.n2 + KF_TILE - 1) / KF_TILE;
-  const int ntiles = p.lower ? tiles_m * (tiles_m + 1) / 2 : tiles_m * p.tiles_n;
+  const int tiles_m = (n1 + KF_TM - 1) / KF_TM;
+  p.tiles_n = (p.n2 + KF_TN - 1) / KF_TN;
+  // lower fill: tile row tm (64 rows) covers column tiles 0 .. tm/2 (128 columns each)
+  int ntiles = tiles_m * p.tiles_n;
+  if (p.lower) {
+    const int q = tiles_m / 2;               // complete pairs of tile rows
+    ntiles = q * (q + 1) + ((tiles_m & 1) ? (q + 1) : 0);
+  }
   kern_fwd_kernel<<<ntiles, KF_THREADS, 0, stream>>>(p);
   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
@@ -262,10 +271,10 @@ int linear_kdiag(const double* X, int n, long ldx, int D, const double* v, doubl
 // backward reductions
 // ================================================================================================
 constexpr int KB_COLS = 128;     // columns (second argument) per CTA, one per thread pair
-constexpr int KB_RT = 16;        // rows per thread per chunk
+constexpr int KB_RT = 8;         // rows per thread per chunk
 constexpr int KB_ROWS = 2 * KB_RT;  // rows per chunk (two thread halves)
 constexpr int KB_THREADS = 256;
-constexpr int KB_DC = 16;        // accumulator chunk of feature dimensions
+// accumulator chunk of feature dimensions (template parameter KB_DC): 8 when D <= 8, else 16
 constexpr int KB_DMAX = 160;     // shared-memory staging limit on D
 constexpr int KB_DY = 8;         // a-vector chunk
 
@@ -283,14 +292,15 @@ struct KbwdParams {
   double* part_g2;   // [strips][n2][D] or nullptr
 };
 
-template <bool GPR>
-__global__ void __launch_bounds__(KB_THREADS) kern_bwd_kernel(const KbwdParams p) {
+// G2: also accumulate the per-column sums needed for dLoss/dX2 (and for the Linear kernel's variance gradient).
+template <bool GPR, int KB_DC, bool G2>
+__global__ void __launch_bounds__(KB_THREADS, 2) kern_bwd_kernel(const KbwdParams p) {
   extern __shared__ double kb_smem[];
   const int D = p.D;
   double* X2s = kb_smem;                       // [D][128]
   double* X1s = X2s + static_cast<size_t>(D) * KB_COLS;    // [KB_ROWS][D]
   double* ellv = X1s + static_cast<size_t>(KB_ROWS) * D;   // [D]
-  double* acol = ellv + D;                     // [128][KB_DY]
+  double* acol = ellv + D;                     // [KB_DY][128]
   double* arow = acol + KB_COLS * KB_DY;       // [KB_ROWS][KB_DY]
   double* red = arow + KB_ROWS * KB_DY;        // [32] + [2][128] combine scratch
   double* comb = red + 32;
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(KB_THREADS) kern_bwd_kernel(const KbwdParams p
           __syncthreads();
           for (int idx = t; idx < KB_COLS * KB_DY; idx += KB_THREADS) {
             const int cc = idx / KB_DY, o = idx - cc * KB_DY;
-            acol[idx] = (c0 + cc < p.n2 && o0 + o < p.dy) ? p.a[static_cast<long>(c0 + cc) * p.lda + o0 + o] : 0.0;
+            acol[o * KB_COLS + cc] = (c0 + cc < p.n2 && o0 + o < p.dy) ? p.a[static_cast<long>(c0 + cc) * p.lda + o0 + o] : 0.0;
           }
           for (int idx = t; idx < KB_ROWS * KB_DY; idx += KB_THREADS) {
             const int rr = idx / KB_DY, o = idx - rr * KB_DY;
@@ -355,7 +365,7 @@ __global__ void __launch_bounds__(KB_THREADS) kern_bwd_kernel(const KbwdParams p
           __syncthreads();
 #pragma unroll
           for (int o = 0; o < KB_DY; ++o) {
-            const double aj = acol[c * KB_DY + o];
+            const double aj = acol[o * KB_COLS + c];
 #pragma unroll
             for (int rr = 0; rr < KB_RT; ++rr) hreg[rr] += arow[(half * KB_RT + rr) * KB_DY + o] * aj;
           }
@@ -423,11 +433,11 @@ __global__ void __launch_bounds__(KB_THREADS) kern_bwd_kernel(const KbwdParams p
           for (int rr = 0; rr < KB_RT; ++rr) {
             const double x1d = X1s[(half * KB_RT + rr) * D + d];
             if (linear) {
-              g2[dd] += hreg[rr] * x1d;
+              if (G2) g2[dd] += hreg[rr] * x1d;
             } else {
               const double diff = x1d - x2d;
               const double u = hreg[rr] * diff;
-              g2[dd] += u;
+              if (G2) g2[dd] += u;
               S[dd] += u * diff;
             }
           }
@@ -443,7 +453,7 @@ __global__ void __launch_bounds__(KB_THREADS) kern_bwd_kernel(const KbwdParams p
       double s = linear ? g2[dd] * X2s[d * KB_COLS + c] : S[dd];
       s = block_sum(s, red);
       if (t == 0) p.part_h[static_cast<long>(cta) * (D + 2) + d] = s;
-      if (p.part_g2) {
+      if (G2 && p.part_g2) {
         __syncthreads();
         comb[half * KB_COLS + c] = g2[dd];
         __syncthreads();
@@ -526,26 +536,36 @@ size_t kern_bwd_workspace_bytes(int n1, int n2, int D) {
   return (ncta * (D + 2) + static_cast<size_t>(strips) * n2 * D) * sizeof(double) + 256;
 }
 
+template <bool GPR, int DC, bool G2>
+static int kbwd_launch_cfg(const KbwdParams& p, int ncb, size_t smem, cudaStream_t stream) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    GPB_CUDA_CHECK(cudaFuncSetAttribute(kern_bwd_kernel<GPR, DC, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  dim3 grid(ncb, p.strips);
+  kern_bwd_kernel<GPR, DC, G2><<<grid, KB_THREADS, smem, stream>>>(p);
+  count_launch();
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
 template <bool GPR>
 static int kbwd_launch(KbwdParams& p, int ncb, double* g_ell, double* g_sigma2, double* g_noise, double* gX2,
                        cudaStream_t stream) {
   const size_t smem = kbwd_smem_bytes(p.D);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    GPB_CUDA_CHECK(cudaFuncSetAttribute(kern_bwd_kernel<GPR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(std::max<size_t>(smem, 64 * 1024))));
-    attr_smem = std::max<size_t>(smem, 64 * 1024);
-  }
-  dim3 grid(ncb, p.strips);
-  kern_bwd_kernel<GPR><<<grid, KB_THREADS, smem, stream>>>(p);
-  count_launch();
-  GPB_CUDA_CHECK(cudaGetLastError());
+  const bool g2 = (gX2 != nullptr) || p.kind == KERN_LINEAR;
+  int rc;
+  if (p.D <= 8) rc = g2 ? kbwd_launch_cfg<GPR, 8, true>(p, ncb, smem, stream) : kbwd_launch_cfg<GPR, 8, false>(p, ncb, smem, stream);
+  else rc = g2 ? kbwd_launch_cfg<GPR, 16, true>(p, ncb, smem, stream) : kbwd_launch_cfg<GPR, 16, false>(p, ncb, smem, stream);
+  if (rc) return rc;
   const int ncta = ncb * p.strips;
   const long work = std::max<long>(p.D + 2, gX2 ? static_cast<long>(p.n2) * p.D : 0);
   const int blocks = static_cast<int>(std::min<long>((work + 255) / 256, 1024));
   kbwd_finalize_kernel<<<blocks, 256, 0, stream>>>(p.kind, p.D, p.ell_len, p.ell, ncta, p.part_h, p.strips, p.n2,
                                                    gX2 ? p.part_g2 : nullptr, g_ell, g_sigma2, g_noise, gX2);
-                                                   count_launch();
+  count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
 }

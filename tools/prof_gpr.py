@@ -12,6 +12,10 @@ noise = torch.full((1,), 0.01, dtype=torch.float64, device=dev)
 buf, ld = nv._aligned_empty(n, n, dev)
 nv.kern_fwd(0, X, None, ell, s2, noise=noise, lower=True, out=buf, ldk=ld)
 dinv, info = nv.potrf_(buf, ld)
+if what == "all":
+    y = torch.randn(n, 1, dtype=torch.float64, device=dev)
+    nv.trsv_(buf, dinv, y, False)
+    nv.trsv_(buf, dinv, y, True)
 if what in ("potri", "all"):
     kd = nv.potri_(buf, ld, dinv)
 if what == "all":
