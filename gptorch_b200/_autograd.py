@@ -310,8 +310,7 @@ class VfeStatsFn(Function):
         kper = VfeStatsFn._k_per_split(min(chunk, n))
         ldm = m + (m & 1)
         AA3 = torch.zeros((VFE_SPLITS, m, ldm), dtype=torch.float64, device=X.device)
-        ldy = dy + (dy & 1)
-        AY3 = torch.zeros((VFE_SPLITS, m, ldy), dtype=torch.float64, device=X.device)
+        AYf = torch.zeros((m, dy), dtype=torch.float64, device=X.device)
         # Keep the solved panels A^T for the backward pass when they fit the budget (N*M*8 bytes); otherwise the
         # backward pass re-streams them from X (one more covariance build + solve per chunk).
         keep = any(ctx.needs_input_grad) and n * ldm * 8 <= VFE_PANEL_CACHE_BYTES
@@ -323,10 +322,9 @@ class VfeStatsFn(Function):
                 cache.append(At)
             with nv.phase("vfe_gram"):
                 nv.gemm_splitk(nv.GEMM_TN, At, At, kper, AA3, beta=1.0, lower_only=True)
-                nv.gemm_splitk(nv.GEMM_TN, At, Y[s:e], kper, AY3, beta=1.0)
+                nv.gemv_t(At, Y[s:e], AYf, beta=1.0)
         AAf = AA3.sum(0)[:, :m]
         AAf = torch.tril(AAf) + torch.tril(AAf, -1).t()
-        AYf = AY3.sum(0)[:, :dy].contiguous()
         # sum_i k(x_i, x_i) = n * sigma2 for a stationary kernel (gptorch/kernels.py:174-179); sum Y^2
         scal = torch.stack([sigma2.reshape(()) * float(n), nv.logdet_sumsq(None, Y)[1]])
         if group is not None:

@@ -279,6 +279,17 @@ def gemm(mode, A, B, alpha=1.0, beta=0.0, C=None, lower_only=False):
     return C
 
 
+def gemv_t(A, Y, out, beta=1.0):
+    """out (cols x dy) = beta * out + A^T Y for a tall row panel A (rows x cols) and few right-hand sides."""
+    A, Y = _c(A), _c(Y)
+    rows, cols = A.shape
+    dy = Y.shape[1]
+    ws = _ws(query("gpb_gemv_t_workspace_bytes", rows, cols), A.device)
+    call("gpb_gemv_t", ptr(A), rows, cols, A.stride(0), ptr(Y), dy, Y.stride(0), float(beta), ptr(out), out.stride(0),
+         ptr(ws), ws.numel() * 8, stream_ptr())
+    return out
+
+
 def gemm_splitk(mode, A, B, k_per_split, C3, beta=1.0, alpha=1.0, lower_only=False):
     """Split-K GEMM: slice s of the k range accumulates into C3[s] (C3: [splits, m, ld] with ld even)."""
     A = _gemm_operand(A)

@@ -17,6 +17,9 @@ int trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace,
 size_t trsv_workspace_bytes(int n);
 int trsv_lower(const double* L, int n, long ldl, const double* dinv, double* B, int k, long ldb, int trans,
                void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t gemv_t_workspace_bytes(long rows, int cols);
+int gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta, double* out,
+           long ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
                  cudaStream_t stream);
 int tri_zero_upper(double* A, int n, long lda, cudaStream_t stream);
@@ -102,6 +105,12 @@ int gpb_trsm_right_lt(const double* L, int n, long ldl, const double* dinv, doub
 int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
                      void* stream) {
   return logdet_sumsq(L, n, ldl, V, vrows, k, ldv, out, S(stream));
+}
+
+size_t gpb_gemv_t_workspace_bytes(long rows, int cols) { return gemv_t_workspace_bytes(rows, cols); }
+int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta,
+               double* out, long ldo, void* workspace, size_t workspace_bytes, void* stream) {
+  return gemv_t(A, rows, cols, lda, Y, dy, ldy, beta, out, ldo, workspace, workspace_bytes, S(stream));
 }
 
 int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,

@@ -25,31 +25,47 @@ __device__ __forceinline__ void st_release_i32(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// y[r] (+)= sum_c T[r][c] * x[c][q]  for a 128 x 128 row-major tile T (ld), rows split over 8 warps, lanes
-// along c (coalesced).  sign = -1 accumulates into accs (accs[r][q] -= ...), mode_out writes result to out.
-template <int KR>
-__device__ __forceinline__ void tile_rowdot(const double* __restrict__ T, long ld, int rows_valid, int cols_valid,
-                                            const double (*xs)[KR], double (*accs)[KR], bool subtract,
-                                            double (*outs)[KR]) {
+// A 128 x 128 row-major tile T (ld) is held in registers as 16 rows per warp x 4 values per lane (lanes along the
+// columns: coalesced).  Loading is separated from the product so that the tile of the NEXT column block is already
+// in flight while the CTA still waits for that block's solution: the loads do not depend on it.
+struct TileRegs { double v[16][4]; };
+
+__device__ __forceinline__ void tile_load(TileRegs& tr, const double* __restrict__ T, long ld, int rows_valid,
+                                          int cols_valid) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll 2
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    const int r = w * 16 + rr;
+    const double* trow = T + static_cast<long>(r) * ld;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int c = lane + 32 * m;
+      tr.v[rr][m] = (r < rows_valid && c < cols_valid) ? __ldcs(trow + c) : 0.0;
+    }
+  }
+}
+
+// y[r] = sum_c T[r][c] * x[c][q]; subtract: accs[r][q] -= y, else outs[r][q] = y.
+template <int KR>
+__device__ __forceinline__ void tile_rowdot(const TileRegs& tr, const double (*xs)[KR], double (*accs)[KR],
+                                            bool subtract, double (*outs)[KR]) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double xr[4][KR];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int q = 0; q < KR; ++q) xr[m][q] = xs[lane + 32 * m][q];
+#pragma unroll
   for (int rr = 0; rr < 16; ++rr) {
     const int r = w * 16 + rr;
     double part[KR];
 #pragma unroll
-    for (int q = 0; q < KR; ++q) part[q] = 0.0;
-    if (r < rows_valid) {
-      const double* trow = T + static_cast<long>(r) * ld;
+    for (int q = 0; q < KR; ++q) {
+      part[q] = 0.0;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int c = lane + 32 * m;
-        const double v = (c < cols_valid) ? __ldcs(trow + c) : 0.0;
-#pragma unroll
-        for (int q = 0; q < KR; ++q) part[q] += v * xs[c][q];
-      }
+      for (int m = 0; m < 4; ++m) part[q] += tr.v[rr][m] * xr[m][q];
+      part[q] = warp_sum(part[q]);
     }
-#pragma unroll
-    for (int q = 0; q < KR; ++q) part[q] = warp_sum(part[q]);
     if (lane == 0) {
 #pragma unroll
       for (int q = 0; q < KR; ++q) {
@@ -78,7 +94,9 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_kernel(const double* __
     const int r = idx / KR, q = idx % KR;
     accs[r][q] = (r < nbi && q < kr) ? B[static_cast<long>(r0 + r) * ldb + col0 + q] : 0.0;
   }
+  TileRegs tr;
   for (int j = 0; j < i; ++j) {
+    tile_load(tr, L + static_cast<long>(r0) * ldl + j * NB, ldl, nbi, NB);   // in flight while waiting below
     if (t == 0) {
       while (ld_acquire_i32(&flags[j]) == 0) { __nanosleep(20); }
     }
@@ -88,16 +106,17 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_kernel(const double* __
       xs[c][q] = (q < kr) ? __ldcg(&B[static_cast<long>(j * NB + c) * ldb + col0 + q]) : 0.0;
     }
     __syncthreads();
-    tile_rowdot<KR>(L + static_cast<long>(r0) * ldl + j * NB, ldl, nbi, NB, xs, accs, true, outs);
+    tile_rowdot<KR>(tr, xs, accs, true, outs);
   }
   __syncthreads();
   // x_i = Inv_ii * acc   (Inv padded with identity; zeros above the diagonal)
+  tile_load(tr, dinv + static_cast<long>(r0) * NB, NB, NB, NB);
   for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
     const int c = idx / KR, q = idx % KR;
     xs[c][q] = accs[c][q];
   }
   __syncthreads();
-  tile_rowdot<KR>(dinv + static_cast<long>(r0) * NB, NB, NB, NB, xs, accs, false, outs);
+  tile_rowdot<KR>(tr, xs, accs, false, outs);
   __syncthreads();
   for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
     const int r = idx / KR, q = idx % KR;
@@ -130,11 +149,19 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_kernel(const double* __
     accs[r][q] = (r < nbi && q < kr) ? B[static_cast<long>(c0 + r) * ldb + col0 + q] : 0.0;
   }
   for (int j = nblk - 1; j > i; --j) {
+    const int nbj = min(NB, n - j * NB);
+    // this thread's 64 rows of the tile L[j][i] (column c): issued before the wait, they do not depend on x_j
+    double lv[64];
+    {
+      const double* tile = L + static_cast<long>(j) * NB * ldl + c0 + c;
+      const int rbeg = half * 64;
+#pragma unroll
+      for (int u = 0; u < 64; ++u) lv[u] = (c < nbi && rbeg + u < nbj) ? __ldcs(tile + static_cast<long>(rbeg + u) * ldl) : 0.0;
+    }
     if (t == 0) {
       while (ld_acquire_i32(&flags[j]) == 0) { __nanosleep(20); }
     }
     __syncthreads();
-    const int nbj = min(NB, n - j * NB);
     for (int idx = t; idx < NB * KR; idx += TRSV_THREADS) {
       const int r = idx / KR, q = idx % KR;
       xs[r][q] = (r < nbj && q < kr) ? __ldcg(&B[static_cast<long>(j * NB + r) * ldb + col0 + q]) : 0.0;
@@ -143,15 +170,10 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_kernel(const double* __
     double p[KR];
 #pragma unroll
     for (int q = 0; q < KR; ++q) p[q] = 0.0;
-    const double* tile = L + static_cast<long>(j) * NB * ldl + c0 + c;
-    const int rbeg = half * 64, rend = min(rbeg + 64, nbj);
-    if (c < nbi) {
-#pragma unroll 8
-      for (int r = rbeg; r < rend; ++r) {
-        const double v = __ldcs(tile + static_cast<long>(r) * ldl);
 #pragma unroll
-        for (int q = 0; q < KR; ++q) p[q] += v * xs[r][q];
-      }
+    for (int u = 0; u < 64; ++u) {
+#pragma unroll
+      for (int q = 0; q < KR; ++q) p[q] += lv[u] * xs[half * 64 + u][q];
     }
 #pragma unroll
     for (int q = 0; q < KR; ++q) part2[half][c][q] = p[q];
@@ -246,6 +268,102 @@ int logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, i
   logdet_sumsq_kernel<<<1, 1024, 0, stream>>>(L, n, ldl, V, vrows, k, ldv, out);
   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[c][o] (+)= sum_r A[r][c] * Y[r][o]   (A: rows x cols, cols contiguous; Y: rows x dy, dy small)
+// The "A Y" statistic of the sparse models for a row panel A^T (gptorch/models/sparse_gpr.py:137): HBM-bound, A is
+// read exactly once.  Thread = one column, two row halves per CTA; per-strip partials are summed in fixed order.
+// ------------------------------------------------------------------------------------------------
+constexpr int GT_THREADS = 256;
+constexpr int GT_DY = 4;
+
+__global__ void __launch_bounds__(GT_THREADS) gemv_t_kernel(const double* __restrict__ A, long rows, int cols, long lda,
+                                                            const double* __restrict__ Y, int dy0, int dy, long ldy,
+                                                            int strips, double* __restrict__ part) {
+  __shared__ double comb[128][GT_DY];
+  const int t = threadIdx.x, c = blockIdx.x * 128 + (t & 127), half = t >> 7;
+  const int strip = blockIdx.y;
+  const long per = (rows + strips - 1) / strips;
+  const long r_begin = strip * per, r_end = min(rows, r_begin + per);
+  const long mid = r_begin + (r_end - r_begin + 1) / 2;
+  const long lo = half == 0 ? r_begin : mid, hi = half == 0 ? mid : r_end;
+  double acc[GT_DY];
+#pragma unroll
+  for (int o = 0; o < GT_DY; ++o) acc[o] = 0.0;
+  if (c < cols) {
+    const double* ap = A + c;
+    long r = lo;
+    for (; r + 8 <= hi; r += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(ap + (r + u) * lda);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int o = 0; o < GT_DY; ++o)
+          if (o < dy) acc[o] += v[u] * __ldg(Y + (r + u) * ldy + dy0 + o);
+      }
+    }
+    for (; r < hi; ++r) {
+      const double v = __ldcs(ap + r * lda);
+#pragma unroll
+      for (int o = 0; o < GT_DY; ++o)
+        if (o < dy) acc[o] += v * __ldg(Y + r * ldy + dy0 + o);
+    }
+  }
+  if (half == 1) {
+#pragma unroll
+    for (int o = 0; o < GT_DY; ++o) comb[t & 127][o] = acc[o];
+  }
+  __syncthreads();
+  if (half == 0 && c < cols) {
+#pragma unroll
+    for (int o = 0; o < GT_DY; ++o)
+      if (o < dy) part[(static_cast<long>(strip) * cols + c) * GT_DY + o] = acc[o] + comb[t & 127][o];
+  }
+}
+
+__global__ void gemv_t_finalize_kernel(const double* __restrict__ part, int strips, int cols, int dy0, int dy,
+                                       double beta, double* __restrict__ out, long ldo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cols * dy) return;
+  const int c = idx / dy, o = idx - c * dy;
+  double s = 0.0;
+  for (int st = 0; st < strips; ++st) s += part[(static_cast<long>(st) * cols + c) * GT_DY + o];
+  double* dst = out + static_cast<long>(c) * ldo + dy0 + o;
+  *dst = (beta != 0.0 ? beta * *dst : 0.0) + s;
+}
+
+static inline int gemv_t_strips(long rows, int cols) {
+  const int ncb = (cols + 127) / 128;
+  long s = (4 * 148 + ncb - 1) / ncb;
+  s = std::max<long>(1, std::min<long>(s, (rows + 255) / 256));
+  return static_cast<int>(s);
+}
+
+size_t gemv_t_workspace_bytes(long rows, int cols) {
+  return static_cast<size_t>(gemv_t_strips(rows, cols)) * cols * GT_DY * sizeof(double) + 64;
+}
+
+int gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta, double* out,
+           long ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (rows < 0 || cols <= 0 || dy <= 0) return GPB_ERR_BADARG;
+  if (!A || !Y || !out || lda < cols || ldy < dy || ldo < dy) return GPB_ERR_BADARG;
+  if (!workspace || workspace_bytes < gemv_t_workspace_bytes(rows, cols)) return GPB_ERR_BADARG;
+  const int strips = gemv_t_strips(rows, cols);
+  double* part = static_cast<double*>(workspace);
+  for (int dy0 = 0; dy0 < dy; dy0 += GT_DY) {
+    const int d = std::min(GT_DY, dy - dy0);
+    dim3 grid((cols + 127) / 128, strips);
+    gemv_t_kernel<<<grid, GT_THREADS, 0, stream>>>(A, rows, cols, lda, Y, dy0, d, ldy, strips, part);
+    count_launch();
+    GPB_CUDA_CHECK(cudaGetLastError());
+    gemv_t_finalize_kernel<<<(cols * d + 255) / 256, 256, 0, stream>>>(part, strips, cols, dy0, d, beta, out, ldo);
+    count_launch();
+    GPB_CUDA_CHECK(cudaGetLastError());
+  }
   return GPB_OK;
 }
 

@@ -142,6 +142,13 @@ int gpb_trsm_right_lt(const double* L, int n, long ldl, const double* dinv, doub
 int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
                      void* stream);
 
+/* out[c][o] = beta * out[c][o] + sum_r A[r][c] * Y[r][o]:  A^T Y for a tall row panel A (rows x cols) and a few
+ * right-hand sides (the "A @ err" statistic of gptorch/models/sparse_gpr.py:137 in row-panel layout).  HBM-bound:
+ * A is read once; deterministic two-stage reduction. */
+size_t gpb_gemv_t_workspace_bytes(long rows, int cols);
+int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta,
+               double* out, long ldo, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- GEMM ------------------------------------------------------------------------------------------------
  * C = alpha * op(A) op(B) + beta * C on the FP64 DMMA engine.  mode: 0 = A B^T (A: m x k, B: n x k),
  * 1 = A^T B (A: k x m, B: k x n), 2 = A B (A: m x k, B: k x n).  lower_only skips tiles above the diagonal

@@ -11,8 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-per-gpu", type=int, default=1250000)
-    ap.add_argument("--m", type=int, default=1024)
-    ap.add_argument("--d", type=int, default=16)
+    ap.add_argument("--num-inducing", dest="m", type=int, default=1024)
+    ap.add_argument("--dim", dest="d", type=int, default=16)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true", help="compare the sharded loss/grads with a single-process run (small N)")
