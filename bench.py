@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: fp64 GPR loss+grad evaluations per second at N=32768, D=8 on B200 (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 32768]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--num-points 32768]
 
 One "step" = one full evaluation of model.loss() + loss.backward() for GPR with an Rbf-ARD kernel on the
 synthetic regression problem of BASELINE.md section 3 (covariance build, Cholesky, solves, log-det, and the
@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=32768, help="training points (the named config is 32768)")
+    ap.add_argument("--num-points", dest="n", type=int, default=32768, help="training points (the named config is 32768)")
     ap.add_argument("--cpu-sample-n", type=int, default=0, help="oracle sample size (0 = choose by core count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -56,8 +56,11 @@ class Model(torch.nn.Module):
                 p.grad.data.zero_()
         loss = self.loss()
         loss.backward()
-        grad = np.concatenate([p.grad.cpu().numpy().flatten() for _, p in self.named_parameters() if p.requires_grad])
-        value = loss.item()
+        # one device-side concatenation and ONE device-to-host copy for loss and all gradients (the reference
+        # copies parameter by parameter, a sync each)
+        pieces = [p.grad.reshape(-1).to(torch.float64) for _, p in self.named_parameters() if p.requires_grad]
+        packed = torch.cat([loss.detach().reshape(-1)[:1].to(torch.float64)] + pieces).cpu().numpy()
+        value, grad = float(packed[0]), packed[1:]
         print("loss: %s" % value)
         finite = np.isfinite(grad)
         if np.all(finite):

@@ -2,3 +2,4 @@
 from .base import GPModel
 from .gpr import GPR
 from .sparse_gpr import VFE, SVGP
+from .dist_gpr import DistributedGPR

@@ -20,6 +20,7 @@ from ..util import as_tensor, kmeans_centers, torch_dtype
 from .base import GPModel
 from .gpr import GPR, _native_kind
 
+MINIBATCH_PERMUTE_MAX = 1 << 22   # above this many rows the minibatch indices are drawn in O(batch)
 VFE_CHUNK_ROWS = 1 << 17   # rows of x per streamed panel (128Ki x M fp64: 1 GiB at M = 1024)
 
 
@@ -132,7 +133,12 @@ def minibatch(loss_func):
         if x is not None:
             assert y is not None
         elif obj.batch_size is not None:
-            i = np.random.permutation(obj.Y.shape[0])[: obj.batch_size]
+            n = obj.Y.shape[0]
+            if n <= MINIBATCH_PERMUTE_MAX:
+                i = np.random.permutation(n)[: obj.batch_size]        # the reference's draw, same RNG stream
+            else:
+                # O(batch) draw without replacement: a full permutation of 1e8 indices per step is 0.8 GB of host work
+                i = np.random.default_rng(np.random.randint(1 << 31)).choice(n, size=obj.batch_size, replace=False)
             i = torch.as_tensor(i, device=obj.X.device)
             x, y = obj.X[i, :], obj.Y[i, :]
         else:

@@ -93,3 +93,22 @@ def _vfe_stats_identity(rank, world):
 def test_vfe_sufficient_statistics_shard_identity():
     errs = _run(_vfe_stats_identity)
     assert max(errs) < 1e-13
+
+
+def test_block_column_cyclic_layout():
+    """Host logic of the distributed Cholesky (gptorch_b200/models/dist_gpr.py): every block column has exactly one
+    owner, slots are dense per rank, ragged last block."""
+    from gptorch_b200.models.dist_gpr import block_columns, local_blocks, owner_of
+    for n, panel, world in ((8300, 1024, 2), (131072, 2048, 8), (1000, 128, 3), (100, 128, 4)):
+        cols = block_columns(n, panel)
+        assert cols[0][0] == 0 and sum(w for _, w in cols) == n and all(w == panel for _, w in cols[:-1])
+        seen = {}
+        for r in range(world):
+            mine, slot = local_blocks(n, panel, r, world)
+            assert sorted(slot.values()) == list(range(len(mine)))
+            for j in mine:
+                assert owner_of(j, world) == r and j not in seen
+                seen[j] = r
+        assert sorted(seen) == list(range(len(cols)))
+        loads = [sum(1 for j in seen if seen[j] == r) for r in range(world)]
+        assert max(loads) - min(loads) <= 1

@@ -1,0 +1,54 @@
+"""Distributed exact-GPR log-likelihood (block-column-cyclic Cholesky over the ranks), BASELINE config #5 shape.
+
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_dist_gpr.py --n 131072
+    torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_dist_gpr.py --n 8300 --panel 1024 --check
+"""
+import argparse, json, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--num-points", dest="n", type=int, default=131072)
+    ap.add_argument("--dim", dest="d", type=int, default=8)
+    ap.add_argument("--panel", type=int, default=2048)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=0)
+    ap.add_argument("--check", action="store_true", help="compare with the single-GPU GPR loss (N must fit one GPU)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+    os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import GPR, DistributedGPR
+    X, Y, _ = O.synth_regression(args.n, args.d)
+    model = DistributedGPR(X.numpy(), Y.numpy(), kernels.Rbf(args.d, ARD=True), likelihood=likelihoods.Gaussian(variance=0.01),
+                           panel=args.panel)
+    for _ in range(args.warmup): model.loss()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps): loss = model.loss()
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    out = {"metric": "distributed GPR log-likelihood evals/s", "n": args.n, "d": args.d, "panel": args.panel, "n_gpus": world,
+           "ms_per_eval": ms.item() / args.steps, "chol_tflops_aggregate": args.n ** 3 / 3.0 / (ms.item() / args.steps) / 1e9,
+           "loss": loss.item(), "max_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    if args.check and rank == 0:
+        ref = GPR(X.numpy(), Y.numpy(), kernels.Rbf(args.d, ARD=True), likelihood=likelihoods.Gaussian(variance=0.01))
+        with torch.no_grad():
+            lref = ref.loss().item()
+        out["single_gpu_loss"] = lref
+        out["check_rel"] = abs(loss.item() - lref) / abs(lref)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.destroy_process_group()
+
+if __name__ == "__main__":
+    main()
