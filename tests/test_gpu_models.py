@@ -273,3 +273,20 @@ def test_optimize_runs():
     assert res.fun < l0
     vfe = VFE(X.numpy(), Y.numpy(), kernels.Rbf(2), num_inducing_points=8)
     vfe.optimize(method="L-BFGS-B", max_iter=3, verbose=False)
+
+
+@pytest.mark.parametrize("model_type,initial,final", [("GPR", 4969.7905, -69.3117), ("VFE", 4969.7974, -69.3109)])
+def test_example_regression_1d_reaches_the_reference_optimum(model_type, initial, final):
+    """BASELINE config #1: the reference's example (N = 100, Linear + Rbf + Constant, L-BFGS-B) goes
+    4969.7905 -> -69.3117 (GPR) and 4969.7974 -> -69.3109 (VFE) [BASELINE.md section 2, measured]."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("regression_1d", os.path.join(ROOT, "examples", "regression_1d.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.run(model_type)
+    assert out["initial_loss"] == pytest.approx(initial, rel=1e-7)
+    assert out["final_loss"] == pytest.approx(final, abs=2e-3)
+    assert out["mu"].shape == (200, 1) and out["var"].shape == (200, 1) and np.all(out["var"] > 0)
+    assert out["samples"].shape == (5, 200, 1)
