@@ -110,11 +110,11 @@ class CholeskyFn(Function):
     def backward(ctx, gL, _g_dinv):
         L, dinv = ctx.saved_tensors
         T = _tinv(L, dinv)
-        P = nv.gemm(nv.GEMM_TN, L, nv._c(gL))  # L^T gL
+        P = nv.gemm(nv.GEMM_TN, L, nv._c(gL), lower_only=True, flags=nv.GF_KLO_M)  # tril(L^T gL), L[k][m] = 0 for k < m
         P.tril_()
         P.diagonal().mul_(0.5)
-        W1 = nv.gemm(nv.GEMM_NT, P, T)         # Phi T^T
-        S = nv.gemm(nv.GEMM_NN, T, W1)         # T Phi T^T = L^-T Phi L^-1
+        W1 = nv.gemm(nv.GEMM_NT, P, T, flags=nv.GF_KHI_M | nv.GF_KLO_N)   # Phi T^T (Phi lower, T upper)
+        S = nv.gemm(nv.GEMM_NN, T, W1, flags=nv.GF_KLO_M)                 # T Phi T^T = L^-T Phi L^-1
         return 0.5 * (S + S.t())
 
 
@@ -166,11 +166,13 @@ class TrsmRightFn(Function):
         L, dinv, out = ctx.saved_tensors
         T = _tinv(L, dinv)
         G = nv._c(G)
-        gX = nv.gemm(nv.GEMM_NT, G, T) if ctx.needs_input_grad[0] else None   # G L^-1 = G T^T
+        # T is upper triangular: (G T^T)[., n] only needs k >= n; -tril(T Q) only needs the lower part of Q
+        gX = nv.gemm(nv.GEMM_NT, G, T, flags=nv.GF_KLO_N) if ctx.needs_input_grad[0] else None   # G L^-1 = G T^T
         gL = None
         if ctx.needs_input_grad[1]:
-            Q = nv.gemm(nv.GEMM_TN, G, out)                  # G^T Out
-            gL = nv.gemm(nv.GEMM_NN, T, Q, alpha=-1.0)       # -L^-T G^T Out
+            Q = nv.gemm(nv.GEMM_TN, G, out, lower_only=True)             # tril(G^T Out)
+            Q.tril_()
+            gL = nv.gemm(nv.GEMM_NN, T, Q, alpha=-1.0, lower_only=True, flags=nv.GF_KLO_M)   # -L^-T G^T Out
             gL.tril_()
         return gX, gL, None
 
@@ -191,13 +193,17 @@ class LogDetFn(Function):
 
 
 class GemmFn(Function):
-    """C = A B^T (NT), A^T B (TN) or A B (NN) on the DMMA engine, differentiable in A and B."""
+    """C = A B^T (NT), A^T B (TN) or A B (NN) on the DMMA engine, differentiable in A and B.
+
+    `b_lower`: B is a square lower-triangular matrix (NN mode only: C = A B with B[k][n] = 0 for k < n).  The zero
+    half of the k-range is skipped in forward and backward, and only the lower part of dB is formed.
+    """
 
     @staticmethod
-    def forward(ctx, mode, A, B):
-        ctx.mode = mode
+    def forward(ctx, mode, A, B, b_lower=False):
+        ctx.mode, ctx.b_lower = mode, bool(b_lower) and mode == nv.GEMM_NN
         ctx.save_for_backward(A, B)
-        return nv.gemm(mode, A, B)
+        return nv.gemm(mode, A, B, flags=nv.GF_KLO_N if ctx.b_lower else 0)
 
     @staticmethod
     @once_differentiable
@@ -212,10 +218,15 @@ class GemmFn(Function):
         elif ctx.mode == nv.GEMM_TN:    # C = A^T B
             if need_a: gA = nv.gemm(nv.GEMM_NT, B, G)
             if need_b: gB = nv.gemm(nv.GEMM_NN, A, G)
+        elif ctx.b_lower:               # C = A B, B lower triangular
+            if need_a: gA = nv.gemm(nv.GEMM_NT, G, B, flags=nv.GF_KHI_N)   # (G B^T)[., n]: B[n][k] = 0 for k > n
+            if need_b:
+                gB = nv.gemm(nv.GEMM_TN, A, G, lower_only=True)
+                gB.tril_()
         else:                           # C = A B
             if need_a: gA = nv.gemm(nv.GEMM_NT, G, B)
             if need_b: gB = nv.gemm(nv.GEMM_TN, A, G)
-        return None, gA, gB
+        return None, gA, gB, None
 
 
 # ------------------------------------------------------------------------------------------------------

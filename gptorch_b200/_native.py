@@ -241,6 +241,7 @@ def logdet_sumsq(L, V=None):
 
 # ---------------------------------------------------------------------------------------------- GEMM
 GEMM_NT, GEMM_TN, GEMM_NN = 0, 1, 2
+GF_LOWER, GF_KLO_M, GF_KHI_M, GF_KLO_N, GF_KHI_N = 1, 2, 4, 8, 16   # include/gpb200.h GPB_GEMM_*
 
 
 def _gemm_operand(t):
@@ -253,8 +254,9 @@ def _gemm_operand(t):
     return t
 
 
-def gemm(mode, A, B, alpha=1.0, beta=0.0, C=None, lower_only=False):
-    """C = alpha op(A) op(B) + beta C on the DMMA engine.  mode: GEMM_NT (A B^T), GEMM_TN (A^T B), GEMM_NN."""
+def gemm(mode, A, B, alpha=1.0, beta=0.0, C=None, lower_only=False, flags=0):
+    """C = alpha op(A) op(B) + beta C on the DMMA engine.  mode: GEMM_NT (A B^T), GEMM_TN (A^T B), GEMM_NN.
+    flags: OR of GF_* (triangular-operand k-range hints, lower tiles only)."""
     A = _gemm_operand(A)
     B = _gemm_operand(B)
     if mode == GEMM_NT:
@@ -275,7 +277,7 @@ def gemm(mode, A, B, alpha=1.0, beta=0.0, C=None, lower_only=False):
         if beta != 0.0:
             raise ValueError("beta != 0 needs an existing C")
     call("gpb_gemm", mode, m, n, k, float(alpha), ptr(A), A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C),
-         C.stride(0), 1 if lower_only else 0, stream_ptr())
+         C.stride(0), int(flags) | (GF_LOWER if lower_only else 0), stream_ptr())
     return C
 
 

@@ -114,7 +114,7 @@ int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, 
 }
 
 int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,
-             double beta, double* C, long ldc, int lower_only, void* stream) {
+             double beta, double* C, long ldc, int flags, void* stream) {
   if (mode < 0 || mode > 2 || m < 0 || n < 0 || k < 0) return GPB_ERR_BADARG;
   if (m == 0 || n == 0) return GPB_OK;
   if (!A || !B || !C) return GPB_ERR_BADARG;
@@ -138,7 +138,8 @@ int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long 
   g.M = m; g.N = n; g.K = k;
   g.alpha = alpha; g.beta = beta;
   g.C = C; g.ldc = ldc;
-  g.flags = lower_only ? GF_LOWER_TILES : 0u;
+  g.flags = static_cast<unsigned>(flags) & (GF_LOWER_TILES | GF_KLO_M | GF_KHI_M | GF_KLO_N | GF_KHI_N);
+  if ((g.flags & GF_LOWER_TILES) && m != n) return GPB_ERR_BADARG;
   return gemm_launch(gm, mapA, mapB, g, S(stream));
 }
 

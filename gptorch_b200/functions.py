@@ -93,6 +93,6 @@ def mm_tn(a, b):
     return ag.GemmFn.apply(nv.GEMM_TN, a, b)
 
 
-def mm(a, b):
-    """a @ b on the native FP64 engine."""
-    return ag.GemmFn.apply(nv.GEMM_NN, a, b)
+def mm(a, b, b_lower=False):
+    """a @ b on the native FP64 engine; b_lower declares b square lower-triangular (its zero half is skipped)."""
+    return ag.GemmFn.apply(nv.GEMM_NN, a, b, b_lower)

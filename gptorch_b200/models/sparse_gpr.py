@@ -209,7 +209,7 @@ class SVGP(_InducingPointsGP):
         beta, t = _whitened if _whitened is not None else self._whitened(chol_kuu)[:2]
         alpha = ag.TrsmRightFn.apply(self.kernel.K(x_new, self.Z), chol_kuu, ag._dinv_of(chol_kuu))   # [n, M]
         f_mean = mm(alpha, t) + self.mean_function(x_new)
-        gamma = mm(alpha, beta)
+        gamma = mm(alpha, beta, b_lower=True)      # beta = L^-1 L_S is lower triangular
         if diag:
             f_cov = (self.kernel.Kdiag(x_new) - torch.sum(alpha ** 2, dim=1) + torch.sum(gamma ** 2, dim=1))[:, None].expand_as(f_mean)
         else:

@@ -151,10 +151,20 @@ int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, 
 
 /* ---- GEMM ------------------------------------------------------------------------------------------------
  * C = alpha * op(A) op(B) + beta * C on the FP64 DMMA engine.  mode: 0 = A B^T (A: m x k, B: n x k),
- * 1 = A^T B (A: k x m, B: k x n), 2 = A B (A: m x k, B: k x n).  lower_only skips tiles above the diagonal
- * (SYRK).  Replaces the `@` products of gptorch/models/sparse_gpr.py:133,137,176,183,360-370. */
+ * 1 = A^T B (A: k x m, B: k x n), 2 = A B (A: m x k, B: k x n).  Replaces the `@` products of
+ * gptorch/models/sparse_gpr.py:133,137,176,183,360-370.
+ * flags (OR of GPB_GEMM_*): LOWER computes only the tiles that intersect the lower triangle (m == n, SYRK);
+ * the K* flags declare a triangular operand so that all-zero k-chunks are skipped, per 128-row/column tile:
+ *   KLO_M: terms with k <  first row of the tile vanish     KHI_M: terms with k >  last row of the tile vanish
+ *   KLO_N: terms with k <  first column of the tile vanish  KHI_N: terms with k >  last column of the tile vanish
+ * (the zero part of the operand must really hold zeros inside the partially covered 128-blocks). */
+#define GPB_GEMM_LOWER 1
+#define GPB_GEMM_KLO_M 2
+#define GPB_GEMM_KHI_M 4
+#define GPB_GEMM_KLO_N 8
+#define GPB_GEMM_KHI_N 16
 int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,
-             double beta, double* C, long ldc, int lower_only, void* stream);
+             double beta, double* C, long ldc, int flags, void* stream);
 
 /* Split-K form: the k range is cut into ceil(k_total / k_per_split) slices (k_per_split a multiple of 16) that run
  * as independent CTAs; slice s accumulates into C + s * c_split_stride.  Used for the Gram products of the sparse
