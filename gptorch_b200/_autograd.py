@@ -153,18 +153,27 @@ class TrsmRightFn(Function):
     @staticmethod
     def forward(ctx, X, L, dinv):
         m, n = X.shape
-        buf, ld = nv._aligned_empty(m, n, X.device)
-        buf[:, :n].copy_(X)
-        nv.trsm_right_lt_(nv._gemm_operand(L), dinv, buf, ld)
-        out = buf[:, :n]
-        ctx.save_for_backward(L, dinv, out)
+        T = None
+        if m >= 2 * n and n >= 2 * nv.NB:
+            # tall panel: one product with the dense inverse factor T = L^-T (upper, k <= n) writes every output
+            # tile once with k up to n; the solve recursion would make log2(n/128) short-k passes over the panel
+            T = _tinv(nv._gemm_operand(L.detach()), dinv)
+            out = nv.gemm(nv.GEMM_NN, X, T, flags=nv.GF_KHI_N)
+        else:
+            buf, ld = nv._aligned_empty(m, n, X.device)
+            buf[:, :n].copy_(X)
+            nv.trsm_right_lt_(nv._gemm_operand(L), dinv, buf, ld)
+            out = buf[:, :n]
+        ctx.has_t = T is not None
+        ctx.save_for_backward(L, dinv, out, T)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, G):
-        L, dinv, out = ctx.saved_tensors
-        T = _tinv(L, dinv)
+        L, dinv, out, T = ctx.saved_tensors
+        if T is None:
+            T = _tinv(L, dinv)
         G = nv._c(G)
         # T is upper triangular: (G T^T)[., n] only needs k >= n; -tril(T Q) only needs the lower part of Q
         gX = nv.gemm(nv.GEMM_NT, G, T, flags=nv.GF_KLO_N) if ctx.needs_input_grad[0] else None   # G L^-1 = G T^T
@@ -315,6 +324,7 @@ class VfeStatsFn(Function):
         X, Y, Z = nv._c(X), nv._c(Y), nv._c(Z)
         Lc = nv._gemm_operand(L)
         dinv = _dinv_of(L)
+        T = _tinv(Lc, dinv)
         n, m, dy = X.shape[0], Z.shape[0], Y.shape[1]
         # The M x M Gram output has only (M/128)^2/2 tiles, far fewer than the GPU has SMs, so the long k = rows
         # dimension is cut into VFE_SPLITS slices that accumulate into separate slots, summed at the end.
@@ -328,7 +338,7 @@ class VfeStatsFn(Function):
         cache = []
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            At, ldat = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, Lc, dinv)
+            At, ldat = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, T)
             if keep:
                 cache.append(At)
             with nv.phase("vfe_gram"):
@@ -344,7 +354,7 @@ class VfeStatsFn(Function):
             torch.distributed.all_reduce(scal, group=group)
         ctx.kind, ctx.chunk, ctx.group, ctx.n_local = kind, chunk, group, n
         ctx.panels = cache if keep else None
-        ctx.save_for_backward(X, Y, Z, ell, sigma2, Lc, dinv, AAf, AYf)
+        ctx.save_for_backward(X, Y, Z, ell, sigma2, T, AAf, AYf)
         return AAf, AYf, scal[0], scal[1]
 
     @staticmethod
@@ -353,25 +363,24 @@ class VfeStatsFn(Function):
         return max(16, (per + 15) // 16 * 16)
 
     @staticmethod
-    def _panel(kind, Xc, Z, ell, sigma2, L, dinv):
+    def _panel(kind, Xc, Z, ell, sigma2, T):
+        """A^T = K(Xc, Z) L^-T for one row chunk, as ONE product with the dense upper-triangular T = L^-T (k <= n):
+        every output tile is written once with k up to M, instead of the solve recursion's many short-k passes."""
         with nv.phase("vfe_kern_fwd"):
             Kfu = nv.kern_fwd(kind, Xc, Z, ell, sigma2)
-        ld = Kfu.stride(0)
         with nv.phase("vfe_trsm"):
-            nv.call("gpb_trsm_right_lt", nv.ptr(L), L.shape[0], L.stride(0), nv.ptr(dinv), nv.ptr(Kfu), Kfu.shape[0], ld,
-                    nv.stream_ptr())
-        return Kfu, ld
+            At = nv.gemm(nv.GEMM_NN, Kfu, T, flags=nv.GF_KHI_N)
+        return At, At.stride(0)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gAA, gAY, g_kd, _g_yy):
-        X, Y, Z, ell, sigma2, L, dinv, AA, AY = ctx.saved_tensors
+        X, Y, Z, ell, sigma2, T, AA, AY = ctx.saved_tensors
         kind, chunk, group = ctx.kind, ctx.chunk, ctx.group
         n = X.shape[0]
         S = nv._c(gAA + gAA.t())
         gAY = nv._c(gAY)
-        T = _tinv(L, dinv)
-        R = nv.gemm(nv.GEMM_NT, S, T)            # S L^-1
+        R = nv.gemm(nv.GEMM_NT, S, T, flags=nv.GF_KLO_N)   # S L^-1 = S T^T
         w = nv.gemm(nv.GEMM_NN, T, gAY)          # L^-T gAY   (m x dy)
         g_ell = torch.zeros_like(ell.reshape(-1))
         g_s2 = torch.zeros(1, dtype=torch.float64, device=X.device)
@@ -383,7 +392,7 @@ class VfeStatsFn(Function):
                 At = panels[ci]
                 panels[ci] = None
             else:
-                At, _ = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, L, dinv)
+                At, _ = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, T)
             with nv.phase("vfe_bwd_gemm"):
                 G = nv.gemm(nv.GEMM_NN, At, R)
                 nv.gemm(nv.GEMM_NT, Y[s:e], w, beta=1.0, C=G)
@@ -399,7 +408,7 @@ class VfeStatsFn(Function):
             g_ell, g_s2, gZ = flat[: g_ell.numel()], flat[g_ell.numel(): g_ell.numel() + 1], flat[g_ell.numel() + 1:].reshape(Z.shape)
         Q = nv.gemm(nv.GEMM_NN, S, AA)
         nv.gemm(nv.GEMM_NT, gAY, AY, beta=1.0, C=Q)
-        gL = nv.gemm(nv.GEMM_NN, T, Q, alpha=-1.0)
+        gL = nv.gemm(nv.GEMM_NN, T, Q, alpha=-1.0, flags=nv.GF_KLO_M)
         gL.tril_()
         return (None, None, None, gZ if ctx.needs_input_grad[3] else None,
                 g_ell.reshape(ell.shape) if ctx.needs_input_grad[4] else None,

@@ -263,11 +263,8 @@ diag_block_kernel(double* __restrict__ A0, long lda, int n, double* __restrict__
 
 static int launch_diag_blocks(double* A0, long lda, int n, double* dinv, int* info, int j_first, int nblocks,
                               int do_factor, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    GPB_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DG_SMEM_BYTES));
-    attr_set = true;
-  }
+  static int smem_state[GPB_MAX_DEVICES] = {0};
+  if (int rc = ensure_dynamic_smem(diag_block_kernel, DG_SMEM_BYTES, smem_state)) return rc;
   diag_block_kernel<<<nblocks, DG_THREADS, DG_SMEM_BYTES, stream>>>(A0, lda, n, dinv, info, j_first, do_factor);
   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());

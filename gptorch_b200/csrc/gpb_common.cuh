@@ -29,6 +29,21 @@ void count_launch(int n = 1);
 long launch_count();
 void reset_launch_count();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember the largest size set for each device.
+// `state` is a per-kernel static array of GPB_MAX_DEVICES ints, zero-initialised.
+constexpr int GPB_MAX_DEVICES = 64;
+template <typename KernelT>
+inline int ensure_dynamic_smem(KernelT kernel, int bytes, int* state) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= GPB_MAX_DEVICES) return GPB_ERR_CUDA;
+  if (bytes > state[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { set_last_error(e, __FILE__, __LINE__); return GPB_ERR_CUDA; }
+    state[dev] = bytes;
+  }
+  return GPB_OK;
+}
+
 // Block size every blocked algorithm in this library is built on (diagonal blocks, Dinv workspace).
 constexpr int NB = 128;
 

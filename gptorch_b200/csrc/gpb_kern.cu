@@ -538,12 +538,8 @@ size_t kern_bwd_workspace_bytes(int n1, int n2, int D) {
 
 template <bool GPR, int DC, bool G2>
 static int kbwd_launch_cfg(const KbwdParams& p, int ncb, size_t smem, cudaStream_t stream) {
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    GPB_CUDA_CHECK(cudaFuncSetAttribute(kern_bwd_kernel<GPR, DC, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    attr_smem = smem;
-  }
+  static int smem_state[GPB_MAX_DEVICES] = {0};
+  if (int rc = ensure_dynamic_smem(kern_bwd_kernel<GPR, DC, G2>, static_cast<int>(smem), smem_state)) return rc;
   dim3 grid(ncb, p.strips);
   kern_bwd_kernel<GPR, DC, G2><<<grid, KB_THREADS, smem, stream>>>(p);
   count_launch();
