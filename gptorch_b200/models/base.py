@@ -74,6 +74,33 @@ def _make_torch_optimizer(method, params, lr):
 class GPModel(Model):
     """Base class of the GP models."""
 
+    # ---- prediction-time cache of factorisations (SURVEY 8f row 1) ---------------------------------------
+    def _param_snapshot(self):
+        """Values of every parameter as one small device vector (compared bit for bit with the cached one: robust
+        against in-place edits of `.data`, which do not bump version counters)."""
+        return torch.cat([p.detach().reshape(-1).to(torch.float64) for p in self.parameters()])
+
+    def _memo(self, name, x, compute):
+        """compute() -- the parameter- and data-dependent part of a prediction (Cholesky factors, solved
+        right-hand sides) -- evaluated once per (parameters, training inputs, targets) state.
+
+        The reference recomputes these on every _predict call (gptorch/models/gpr.py:104,
+        gptorch/models/sparse_gpr.py:169-183, :358).  Only active under torch.no_grad(): with autograd enabled the
+        result is recomputed so that predictions stay differentiable exactly as in the reference.  The key is the
+        identity of the data (storage + in-place version counters) plus a bit-exact parameter snapshot.
+        """
+        if torch.is_grad_enabled():
+            return compute()
+        key = ((x.data_ptr(), x._version, tuple(x.shape)), (self.Y.data_ptr(), self.Y._version, tuple(self.Y.shape)))
+        snap = self._param_snapshot()
+        store = self.__dict__.setdefault("_memo_store", {})
+        hit = store.get(name)
+        if hit is not None and hit[0] == key and hit[1].shape == snap.shape and torch.equal(hit[1], snap):
+            return hit[2]
+        value = compute()
+        store[name] = (key, snap, value)
+        return value
+
     def __init__(self, x, y, kernel, likelihood, mean_function, name="gp"):
         super().__init__()
         self.kernel = kernel

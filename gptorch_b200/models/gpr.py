@@ -56,33 +56,18 @@ class GPR(GPModel):
         n = x.shape[0]
         return self.kernel.K(x) + noise * torch.eye(n, dtype=x.dtype, device=x.device)
 
-    def _factor_key(self, x):
-        """Identity of the data the factorisation depends on (storage + in-place version counters)."""
-        return ((x.data_ptr(), x._version, tuple(x.shape)), (self.Y.data_ptr(), self.Y._version))
-
-    def _param_snapshot(self):
-        """Values of every parameter as one small device vector (compared bit for bit with the cached one: robust
-        against in-place edits of `.data`, which do not bump version counters)."""
-        return torch.cat([p.detach().reshape(-1).to(torch.float64) for p in self.parameters()])
-
     def _factor(self, x):
         """L = chol(Ky) and V = L^-1 (Y - m(x)).
 
         The reference re-factorises on every _predict call (gptorch/models/gpr.py:104).  Under torch.no_grad() the
-        factor is cached and reused while parameters and data are unchanged; with autograd
-        enabled it is recomputed so that predictions stay differentiable exactly as in the reference.
+        factor is cached and reused while parameters and data are unchanged (GPModel._memo); with
+        autograd enabled it is recomputed so that predictions stay differentiable exactly as in the reference.
         """
-        if torch.is_grad_enabled():
+        def compute():
             L = cholesky(self._compute_kyy(x=x))
             return L, trtrs(self.Y - self.mean_function(x), L)
-        key, snap = self._factor_key(x), self._param_snapshot()
-        cached = getattr(self, "_factor_cache", None)
-        if cached is not None and cached[0] == key and cached[1].shape == snap.shape and torch.equal(cached[1], snap):
-            return cached[2], cached[3]
-        L = cholesky(self._compute_kyy(x=x))
-        V = trtrs(self.Y - self.mean_function(x), L)
-        self._factor_cache = (key, snap, L, V)
-        return L, V
+
+        return self._memo("factor", x, compute)
 
     def _predict(self, x_new, diag=True, x=None):
         """p(f* | y): mean [n*, dy] and variance [n*, dy] (diag) or covariance [n*, n*]

@@ -115,7 +115,8 @@ class VFE(_InducingPointsGP):
         """p(f* | y) with the inducing outputs integrated out (gptorch/models/sparse_gpr.py:155-195).
         Unlike the reference this does not freeze Z as a side effect."""
         x = x if x is not None else self.X
-        noise, L, AAT, LB, c, _, _ = self._core(x)
+        # O(N M^2) part: streamed once per parameter state under no_grad (the reference recomputes it per call)
+        noise, L, AAT, LB, c, _, _ = self._memo("core", x, lambda: self._core(x))
         T1 = ag.TrsmRightFn.apply(self.kernel.K(x_new, self.Z), L, ag._dinv_of(L))     # (L^-1 Kus)^T
         T2 = ag.TrsmRightFn.apply(T1, LB, ag._dinv_of(LB))                             # (LB^-1 L^-1 Kus)^T
         mean = mm(T2, c)
@@ -205,8 +206,14 @@ class SVGP(_InducingPointsGP):
 
     def _predict(self, x_new, diag=True, chol_kuu=None, _whitened=None, **kwargs):
         """q(f*) mean [n, dy] and variance [n, dy] / covariance [n, n] (gptorch/models/sparse_gpr.py:337-381)."""
-        chol_kuu = cholesky(self.kernel.K(self.Z)) if chol_kuu is None else chol_kuu
-        beta, t = _whitened if _whitened is not None else self._whitened(chol_kuu)[:2]
+        if chol_kuu is None and _whitened is None:
+            def compute():
+                L = cholesky(self.kernel.K(self.Z))
+                return (L,) + tuple(self._whitened(L)[:2])
+            chol_kuu, beta, t = self._memo("whitened", self.X, compute)
+        else:
+            chol_kuu = cholesky(self.kernel.K(self.Z)) if chol_kuu is None else chol_kuu
+            beta, t = _whitened if _whitened is not None else self._whitened(chol_kuu)[:2]
         alpha = ag.TrsmRightFn.apply(self.kernel.K(x_new, self.Z), chol_kuu, ag._dinv_of(chol_kuu))   # [n, M]
         f_mean = mm(alpha, t) + self.mean_function(x_new)
         gamma = mm(alpha, beta, b_lower=True)      # beta = L^-1 L_S is lower triangular

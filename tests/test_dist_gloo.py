@@ -112,3 +112,94 @@ def test_block_column_cyclic_layout():
         assert sorted(seen) == list(range(len(cols)))
         loads = [sum(1 for j in seen if seen[j] == r) for r in range(world)]
         assert max(loads) - min(loads) <= 1
+
+
+class _TorchOps:
+    """Test-only stand-in for gptorch_b200.models.dist_gpr.NativeOps: the same primitive contract on torch CPU
+    tensors (the oracle's arithmetic), so that the block-column-cyclic bookkeeping of the distributed Cholesky /
+    inverse / gradient can run under gloo.  Lives in tests/ -- the product has no CPU path."""
+
+    block = 1
+    GEMM_NT, GEMM_TN, GEMM_NN = 0, 1, 2
+    NAMES = {0: "Rbf", 1: "Exp", 2: "Matern32", 3: "Matern52"}
+
+    def empty(self, rows, cols, device):
+        return torch.full((rows, cols), float("nan"), dtype=torch.float64)
+
+    def kern_fill(self, kind, Xr, Xc, ell, s2, out, ld):
+        from oracle import gp_oracle as O
+        out[:, : Xc.shape[0]] = O.cov(self.NAMES[kind], Xr, Xc, ell, s2)
+
+    def add_diag(self, blk, ld, value):
+        blk.diagonal().add_(value.reshape(()))
+
+    def factor_panel(self, blk, wp, ld):
+        L = torch.linalg.cholesky(torch.tril(blk[:wp, :wp]) + torch.tril(blk[:wp, :wp], -1).t())
+        blk[:wp, :wp] = L + torch.triu(torch.full_like(L, 7.0), 1)     # native potrf leaves scratch above the diagonal
+        if blk.shape[0] > wp:
+            blk[wp:, :wp] = torch.linalg.solve_triangular(L, blk[wp:, :wp].t().contiguous(), upper=False).t()
+        return torch.zeros(1, dtype=torch.int32)
+
+    def solve_lower(self, Lpp, xp):
+        xp.copy_(torch.linalg.solve_triangular(torch.tril(Lpp), xp.contiguous(), upper=False))
+
+    def logdet(self, Lpp):
+        return Lpp.diagonal().log().sum()
+
+    def sumsq(self, v):
+        return v.pow(2).sum()
+
+    def tri_inverse_t(self, Lpp):
+        n = Lpp.shape[0]
+        return torch.linalg.solve_triangular(torch.tril(Lpp), torch.eye(n, dtype=torch.float64), upper=False).t().contiguous()
+
+    def gemm(self, mode, A, B, alpha=1.0, beta=0.0, C=None, flags=0):
+        prod = A @ B.t() if mode == 0 else (A.t() @ B if mode == 1 else A @ B)
+        if C is None:
+            return alpha * prod
+        C.copy_(alpha * prod + (beta * C if beta != 0.0 else 0.0))
+        return C
+
+    def gemv_t(self, A, Y, out):
+        out.copy_(A.t() @ Y)
+        return out
+
+    def kern_bwd(self, kind, Xr, Xc, ell, s2, G):
+        from oracle import gp_oracle as O
+        e = ell.detach().clone().requires_grad_(True)
+        s = s2.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            (O.cov(self.NAMES[kind], Xr, Xc, e, s) * G).sum().backward()
+        return e.grad, s.grad
+
+
+def _dist_gpr_loss_and_grad(rank, world, n=203, panel=32, kind="Matern52"):
+    from oracle import gp_oracle as O
+    from gptorch_b200 import settings, kernels, likelihoods
+    from gptorch_b200.models import DistributedGPR
+    settings.set_default_device("cpu")
+    d = 3
+    X, Y, _ = O.synth_regression(n, d)
+    ell, var, noise = [0.6, 0.9, 1.3], 1.7, 0.05
+    kern = getattr(kernels, kind)(d, ARD=True, length_scales=np.array(ell), variance=var)
+    model = DistributedGPR(X.numpy(), Y.numpy(), kern, likelihood=likelihoods.Gaussian(variance=noise), panel=panel,
+                           ops=_TorchOps())
+    loss = model.loss()
+    loss.sum().backward()
+    ref_loss, ref = O.gpr_loss_and_grads(kind, X, Y, ell, var, noise)
+    got = {"variance": model.kernel.variance.grad, "length_scales": model.kernel.length_scales.grad,
+           "noise": model.likelihood.variance.grad}
+    rel = lambda a, b: float((a.reshape(-1) - b.reshape(-1)).abs().max() / b.abs().max())  # noqa: E731
+    return (abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()), {k: rel(got[k], ref[k]) for k in ref})
+
+
+@pytest.mark.parametrize("world,n,panel", [(2, 203, 32), (3, 130, 16), (2, 64, 64)])
+def test_distributed_gpr_gradient_bookkeeping(world, n, panel):
+    """Block-column-cyclic Cholesky -> T = L^-1 -> Ky^-1 = T^T T -> gradient reduction, on `world` gloo ranks with the
+    torch stand-in for the native primitives, against the oracle's autograd (ragged last block, more ranks than
+    blocks' worth of look-ahead, a single block)."""
+    import functools
+    out = _run(functools.partial(_dist_gpr_loss_and_grad, n=n, panel=panel), world=world)
+    for loss_err, grad_err in out:
+        assert loss_err < 1e-12
+        assert max(grad_err.values()) < 1e-9, grad_err

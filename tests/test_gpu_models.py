@@ -290,3 +290,56 @@ def test_example_regression_1d_reaches_the_reference_optimum(model_type, initial
     assert out["final_loss"] == pytest.approx(final, abs=2e-3)
     assert out["mu"].shape == (200, 1) and out["var"].shape == (200, 1) and np.all(out["var"] > 0)
     assert out["samples"].shape == (5, 200, 1)
+
+
+@pytest.mark.parametrize("family", ["GPR", "VFE", "SVGP"])
+def test_predict_factor_cache(family):
+    """under no_grad the parameter-dependent factorisations of _predict are computed once per
+    parameter/data state -- the second call launches fewer kernels and returns identical numbers; changing a
+    hyper-parameter (even through .data) or the targets invalidates the cache; with autograd on nothing is cached."""
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods, _native as nv
+    from gptorch_b200.models import GPR, VFE, SVGP
+    X, Y, g = O.synth_regression(700, 3)
+    Z = O.synth_inducing(X, 40, g).numpy()
+    np.random.seed(0)
+
+    def build():
+        kern = kernels.Matern52(3, ARD=True, length_scales=np.array([0.6, 0.9, 1.2]), variance=1.4)
+        lik = likelihoods.Gaussian(variance=0.05)
+        if family == "GPR":
+            return GPR(X.numpy(), Y.numpy(), kern, likelihood=lik)
+        if family == "VFE":
+            return VFE(X.numpy(), Y.numpy(), kern, inducing_points=Z, likelihood=lik)
+        return SVGP(X.numpy(), Y.numpy(), kern, inducing_points=Z, likelihood=lik)
+
+    model = build()
+    xs = torch.rand(50, 3, dtype=torch.float64, generator=g).cuda()
+    with torch.no_grad():
+        nv.reset_launch_count()
+        m1, v1 = model._predict(xs, diag=True)
+        first = nv.launch_count()
+        nv.reset_launch_count()
+        m2, v2 = model._predict(xs, diag=True)
+        second = nv.launch_count()
+        assert second < first
+        assert torch.equal(m1, m2) and torch.equal(v1, v2)
+        # a parameter edit through .data (no version bump) must invalidate
+        model.kernel.variance.data += 0.3
+        m3, _ = model._predict(xs, diag=True)
+        fresh = build()
+        fresh.kernel.variance.data += 0.3
+        if family == "SVGP":            # q(u) is initialised from random points: share it
+            fresh.induced_output_mean.data.copy_(model.induced_output_mean.data)
+            fresh.induced_output_chol_cov.data.copy_(model.induced_output_chol_cov.data)
+        m4, _ = fresh._predict(xs, diag=True)
+        assert not torch.equal(m3, m1)
+        assert rel_err(m3.cpu().numpy(), m4.cpu().numpy()) < 1e-12
+        if family != "SVGP":            # SVGP's posterior does not read Y at prediction time
+            model.Y.mul_(2.0)
+            m5, _ = model._predict(xs, diag=True)
+            assert rel_err(m5.cpu().numpy(), 2.0 * m3.cpu().numpy()) < 1e-9
+    # autograd on: recomputed, differentiable
+    mu, _ = model._predict(xs, diag=True)
+    mu.sum().backward()
+    assert model.kernel.length_scales.grad is not None

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--check", action="store_true", help="compare with the single-GPU GPR loss (N must fit one GPU)")
+    ap.add_argument("--grad", action="store_true", help="time loss + backward (distributed inverse and gradient)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lr = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(lr)
@@ -28,22 +29,37 @@ def main():
     X, Y, _ = O.synth_regression(args.n, args.d)
     model = DistributedGPR(X.numpy(), Y.numpy(), kernels.Rbf(args.d, ARD=True), likelihood=likelihoods.Gaussian(variance=0.01),
                            panel=args.panel)
-    for _ in range(args.warmup): model.loss()
+    params = [p for p in model.parameters() if p.requires_grad]
+    def evaluate():
+        if not args.grad:
+            with torch.no_grad():
+                return model.loss()
+        for p in params: p.grad = None
+        loss = model.loss()
+        loss.sum().backward()
+        return loss.detach()
+    for _ in range(args.warmup): evaluate()
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps): loss = model.loss()
+    for _ in range(args.steps): loss = evaluate()
     e1.record()
     dist.barrier(); torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    out = {"metric": "distributed GPR log-likelihood evals/s", "n": args.n, "d": args.d, "panel": args.panel, "n_gpus": world,
-           "ms_per_eval": ms.item() / args.steps, "chol_tflops_aggregate": args.n ** 3 / 3.0 / (ms.item() / args.steps) / 1e9,
+    out = {"metric": "distributed GPR loss+grad evals/s" if args.grad else "distributed GPR log-likelihood evals/s", "n": args.n, "d": args.d, "panel": args.panel, "n_gpus": world,
+           "ms_per_eval": ms.item() / args.steps, "tflops_aggregate": args.n ** 3 / (1.0 if args.grad else 3.0) / (ms.item() / args.steps) / 1e9,
            "loss": loss.item(), "max_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
     if args.check and rank == 0:
         ref = GPR(X.numpy(), Y.numpy(), kernels.Rbf(args.d, ARD=True), likelihood=likelihoods.Gaussian(variance=0.01))
-        with torch.no_grad():
-            lref = ref.loss().item()
+        if args.grad:
+            l1 = ref.loss(); l1.sum().backward(); lref = l1.item()
+            rp = [p for p in ref.parameters() if p.requires_grad]
+            out["grad_check_rel"] = max(float((a.grad - b.grad).abs().max() / b.grad.abs().max()) for a, b in zip(params, rp))
+            out["grads"] = [p.grad.flatten().tolist() for p in params]
+        else:
+            with torch.no_grad():
+                lref = ref.loss().item()
         out["single_gpu_loss"] = lref
         out["check_rel"] = abs(loss.item() - lref) / abs(lref)
     if rank == 0:
