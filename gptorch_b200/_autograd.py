@@ -78,6 +78,73 @@ class KernelFn(Function):
         return None, gX, gX2, g_ell, g_s2, g_noise
 
 
+def _spec_terms(spec, params):
+    """Resolve a composite spec -- terms of (kind, ell index or -1, sigma2 index or -1) -- against `params`."""
+    return [[(k, params[ie] if ie >= 0 else None, params[isg] if isg >= 0 else None) for (k, ie, isg) in term]
+            for term in spec]
+
+
+def _composite_grads(spec, X, X2, params, G, need_x, need_x2):
+    """Backward of K = sum_t prod_{l in t} k_l(X, X2) for an upstream gradient G: returns ([grad per param], gX, gX2).
+
+    Leaf l of term t sees the upstream gradient G .* prod_{l' != l in t} k_l'; the product of the other leaves is
+    formed by one composite forward pass (the only N x N temporary, and only for Product terms) and multiplied into
+    G on the fly by gpb_kern_bwd_mul.  Sum terms (a single leaf) read G directly."""
+    sym = X2 is None
+    grads = [None] * len(params)
+    gX = gX2 = None
+
+    def add(i, g, like):
+        if i < 0:
+            return
+        g = g.reshape(like.shape)
+        grads[i] = g if grads[i] is None else grads[i] + g
+
+    for term in spec:
+        for li, (kind, ie, isg) in enumerate(term):
+            others = [leaf for lj, leaf in enumerate(term) if lj != li]
+            Mul = nv.kern_sop_fwd(_spec_terms([others], params), X, X2) if others else None
+            ell = params[ie] if ie >= 0 else None
+            s2 = params[isg] if isg >= 0 else None
+            has_x = kind < nv.KERN_CONSTANT
+            want_col = has_x and (need_x2 or (sym and need_x))
+            g_ell, g_s2, g_col = nv.kern_bwd_mul(kind, X, X2, ell, s2, G, Mul, want_col, symmetric=sym)
+            if ie >= 0:
+                add(ie, g_ell, params[ie])
+            if isg >= 0:
+                add(isg, g_s2, params[isg])
+            if has_x and need_x:
+                _, _, g_row = nv.kern_bwd_mul(kind, X if sym else X2, X, ell, s2, G, Mul, True, g_transposed=True,
+                                              symmetric=sym)
+                contrib = g_row + g_col if sym else g_row
+                gX = contrib if gX is None else gX + contrib
+            if has_x and need_x2 and not sym:
+                gX2 = g_col if gX2 is None else gX2 + g_col
+    return grads, gX, gX2
+
+
+class CompositeKernelFn(Function):
+    """Sum / Product trees of leaf kernels (gptorch/kernels.py:286-306) in sum-of-products normal form, evaluated by
+    ONE pass of gpb_kern_sop_fwd; with `noise` (and X2 None) it is Ky of GPR._compute_kyy."""
+
+    @staticmethod
+    def forward(ctx, spec, X, X2, noise, *params):
+        ctx.spec = spec
+        ctx.save_for_backward(X, X2, *params)
+        return nv.kern_sop_fwd(_spec_terms(spec, params), X, X2, noise=noise if X2 is None else None)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        X, X2, *params = ctx.saved_tensors
+        G = nv._c(G)
+        need = ctx.needs_input_grad
+        grads, gX, gX2 = _composite_grads(ctx.spec, X, X2, params, G, need[1], need[2] and X2 is not None)
+        g_noise = G.diagonal().sum().reshape(1) if need[3] else None
+        grads = [g if need[4 + i] else None for i, g in enumerate(grads)]
+        return (None, gX, gX2, g_noise) + tuple(grads)
+
+
 # ------------------------------------------------------------------------------------------------------
 # Cholesky and solves
 # ------------------------------------------------------------------------------------------------------
@@ -304,6 +371,61 @@ class GPRLogLikFn(Function):
         out_noise = (-g) * g_noise.reshape(-1) if ctx.needs_input_grad[5] else None
         out_resid = (-g) * a if ctx.needs_input_grad[2] else None
         return None, None, out_resid, out_ell, out_s2, out_noise
+
+
+class GPRCompositeLogLikFn(Function):
+    """GPR.log_likelihood with a composite kernel (BASELINE config #1: Linear + Rbf + Constant,
+    examples/regression_1d.py:42) as one node: same N^3-flop structure as GPRLogLikFn -- potrf, blocked inverse --
+    with W = 1/2 (dy Kinv - a a^T) assembled once (dense, symmetric) and reduced leaf by leaf by _composite_grads."""
+
+    @staticmethod
+    def forward(ctx, spec, X, resid, noise, *params):
+        n, dy = resid.shape
+        X = nv._c(X)
+        buf, ld = nv._aligned_empty(n, n, X.device)
+        terms = _spec_terms(spec, params)
+        for attempt in range(JITTER_TRIES + 1):
+            with nv.phase("kern_fwd"):
+                nv.kern_sop_fwd(terms, X, None, noise=noise, lower=True, out=buf, ldk=ld)
+            if attempt > 0:
+                nv.add_diag_(buf, ld, 10.0 ** (-JITTER_TRIES + attempt - 1))
+            with nv.phase("potrf"):
+                dinv, info = nv.potrf_(buf, ld)
+            if int(info.item()) == 0:
+                break
+        else:
+            raise RuntimeError("Max tries exceeded.")
+        with nv.phase("solve_logdet"):
+            alpha = nv._c(resid).clone()
+            nv.trsv_(buf, dinv, alpha, False)
+            red = nv.logdet_sumsq(buf, alpha)
+        loglik = (-0.5 * red[1] - dy * red[0] - 0.5 * dy * n * math.log(2.0 * math.pi)).reshape(1)
+        ctx.spec, ctx.ld, ctx.used = spec, ld, False
+        ctx.save_for_backward(X, buf, dinv, alpha, *params)
+        return loglik
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        if ctx.used:
+            raise RuntimeError("GPRCompositeLogLikFn: the factor buffer was consumed by a previous backward pass")
+        ctx.used = True
+        X, buf, dinv, alpha, *params = ctx.saved_tensors
+        dy = alpha.shape[1]
+        with nv.phase("solve_logdet"):
+            a = alpha.clone()
+            nv.trsv_(buf, dinv, a, True)
+        with nv.phase("potri"):
+            kd = nv.potri_(buf, ctx.ld, dinv)
+            W = nv.potri_assemble(buf, ctx.ld, kd)                                   # full symmetric Ky^-1
+        with nv.phase("gpr_grad"):
+            nv.gemm(nv.GEMM_NT, a, a, alpha=-0.5, beta=0.5 * dy, C=W)                # W = 1/2 (dy Kinv - a a^T)
+            grads, _, _ = _composite_grads(ctx.spec, X, None, params, W, False, False)
+            g_noise = W.diagonal().sum().reshape(1)
+        g = g.reshape(())
+        need = ctx.needs_input_grad
+        return (None, None, (-g) * a if need[2] else None, (-g) * g_noise if need[3] else None) + tuple(
+            ((-g) * gr if (gr is not None and need[4 + i]) else None) for i, gr in enumerate(grads))
 
 
 # ------------------------------------------------------------------------------------------------------

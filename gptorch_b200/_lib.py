@@ -34,6 +34,11 @@ SIGNATURES = {
     "gpb_kern_bwd": (c_int, [c_int, c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_int,
                              c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                              c_void_p]),
+    "gpb_kern_bwd_mul": (c_int, [c_int, c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_long, c_int, c_void_p, c_long, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gpb_kern_sop_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_long,
+                                 c_void_p, c_int, c_long, c_int, c_void_p, c_int, c_void_p, c_long, c_void_p]),
     "gpb_linear_kdiag": (c_int, [c_void_p, c_int, c_long, c_int, c_void_p, c_void_p, c_void_p]),
     "gpb_potrf_lower": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_void_p]),
     "gpb_tri_diag_inverse": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p]),

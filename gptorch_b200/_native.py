@@ -61,8 +61,10 @@ def launch_count():
 def reset_launch_count():
     _lib.load().gpb_reset_launch_count()
 
-KIND = {"Rbf": 0, "SquaredExponential": 0, "Exp": 1, "Matern12": 1, "Matern32": 2, "Matern52": 3, "Linear": 4}
-KERN_LINEAR = 4
+KIND = {"Rbf": 0, "SquaredExponential": 0, "Exp": 1, "Matern12": 1, "Matern32": 2, "Matern52": 3, "Linear": 4,
+        "Periodic": 5, "Constant": 6, "Bias": 6, "White": 7}
+KERN_LINEAR, KERN_CONSTANT, KERN_WHITE = 4, 6, 7
+SOP_MAX_TERMS, SOP_MAX_LEAVES = 8, 16      # gpb_kern_sop_fwd limits (include/gpb200.h)
 
 
 def _c(t):
@@ -134,6 +136,70 @@ def kern_bwd(kind, X, X2, ell, sigma2, G, need_gx2, g_transposed=False):
     return g_ell, g_sig, gX2
 
 
+def kern_bwd_mul(kind, X, X2, ell, sigma2, G, Mul, need_gx2, g_transposed=False, symmetric=False):
+    """kern_bwd with the upstream gradient G .* Mul (Mul may be None); also handles Constant / White leaves.
+    Returns (g_ell, g_sigma2, gX2 or None)."""
+    X = _c(X)
+    n1, D = X.shape
+    X2c = _c(X2) if X2 is not None else X
+    n2 = X2c.shape[0]
+    if ell is None:
+        ell = torch.ones(1, dtype=torch.float64, device=X.device)
+    ell = _c(ell).reshape(-1)
+    G = _c(G)
+    Mul = _c(Mul) if Mul is not None else None
+    g_ell = torch.empty(ell.numel(), dtype=torch.float64, device=X.device)
+    g_sig = torch.empty(1, dtype=torch.float64, device=X.device)
+    gX2 = torch.empty((n2, D), dtype=torch.float64, device=X.device) if need_gx2 else None
+    ws = _ws(query("gpb_kern_bwd_workspace_bytes", n1, n2, D), X.device)
+    call("gpb_kern_bwd_mul", kind, ptr(X), n1, X.stride(0), ptr(X2c), n2, X2c.stride(0), D, ptr(ell), ell.numel(),
+         ptr(_c(sigma2).reshape(-1)) if sigma2 is not None else None, ptr(G), G.stride(0), 1 if g_transposed else 0,
+         ptr(Mul), Mul.stride(0) if Mul is not None else 0, 1 if (symmetric or X2 is None) else 0,
+         ptr(g_ell), ptr(g_sig), ptr(gX2), ptr(ws), ws.numel() * 8, stream_ptr())
+    return g_ell, g_sig, gX2
+
+
+def kern_sop_fwd(terms, X, X2, noise=None, lower=False, out=None, ldk=None):
+    """K = sum over terms of the product of the term's leaves, in one pass.  terms: list of lists of
+    (kind, ell or None, sigma2 or None) with device tensors."""
+    import ctypes
+    X = _c(X)
+    n1, D = X.shape
+    if X2 is not None:
+        X2 = _c(X2)
+        n2 = X2.shape[0]
+        if X2.shape[1] != D:
+            raise ValueError("X and X2 have different input dimensions")
+    else:
+        n2 = n1
+    leaves = [leaf for term in terms for leaf in term]
+    if not terms or len(terms) > SOP_MAX_TERMS or len(leaves) > SOP_MAX_LEAVES:
+        raise ValueError("composite kernel: at most %d terms / %d leaves" % (SOP_MAX_TERMS, SOP_MAX_LEAVES))
+    if out is None:
+        out, ldk = _aligned_empty(n1, n2, X.device)
+    if n1 == 0 or n2 == 0:
+        return out[:, :n2]
+    keep = []   # keep the contiguous parameter copies alive until the launch has been issued
+
+    def dev_ptr(t):
+        if t is None:
+            return None
+        t = _c(t).reshape(-1)
+        keep.append(t)
+        return ptr(t).value
+
+    nl = len(leaves)
+    term_len = (ctypes.c_int * len(terms))(*[len(t) for t in terms])
+    kinds = (ctypes.c_int * nl)(*[int(k) for k, _, _ in leaves])
+    ells = (ctypes.c_void_p * nl)(*[dev_ptr(e) for _, e, _ in leaves])
+    ell_len = (ctypes.c_int * nl)(*[(e.numel() if e is not None else 0) for _, e, _ in leaves])
+    sig = (ctypes.c_void_p * nl)(*[dev_ptr(s) for _, _, s in leaves])
+    call("gpb_kern_sop_fwd", len(terms), term_len, kinds, ells, ell_len, sig, ptr(X), n1, X.stride(0), ptr(X2), n2,
+         X2.stride(0) if X2 is not None else 0, D, ptr(_c(noise).reshape(-1)) if noise is not None else None,
+         1 if lower else 0, ptr(out), ldk, stream_ptr())
+    return out[:, :n2]
+
+
 def linear_kdiag(X, v):
     X = _c(X)
     out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
@@ -181,9 +247,9 @@ def trtri_upper_(A, lda, dinv):
 
 def potri_assemble(A, lda, kd):
     n = A.shape[0]
-    out = torch.empty((n, n), dtype=torch.float64, device=A.device)
-    call("gpb_potri_assemble", ptr(A), n, lda, ptr(kd), ptr(out), n, stream_ptr())
-    return out
+    out, ldo = _aligned_empty(n, n, A.device)
+    call("gpb_potri_assemble", ptr(A), n, lda, ptr(kd), ptr(out), ldo, stream_ptr())
+    return out[:, :n]
 
 
 def tri_zero_upper_(A, lda):

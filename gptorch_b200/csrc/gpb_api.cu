@@ -32,6 +32,14 @@ int kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int 
              const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
              double* g_ell, double* g_sigma2, double* gX2, void* workspace, size_t workspace_bytes,
              cudaStream_t stream);
+int kern_bwd_mul(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                 const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
+                 const double* Mul, long ldm, int symmetric, double* g_ell, double* g_sigma2, double* gX2,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int kern_sop_fwd(int n_terms, const int* term_len, const int* leaf_kind, const double* const* leaf_ell,
+                 const int* leaf_ell_len, const double* const* leaf_sigma2, const double* X, int n1, long ldx,
+                 const double* X2, int n2, long ldx2, int D, const double* noise, int fill, double* K, long ldk,
+                 cudaStream_t stream);
 int linear_kdiag(const double* X, int n, long ldx, int D, const double* v, double* out, cudaStream_t stream);
 size_t gpr_grad_workspace_bytes(int n, int D);
 int gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* ell, int ell_len,
@@ -64,6 +72,20 @@ int gpb_kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, 
                  void* stream) {
   return kern_bwd(kind, X, n1, ldx, X2, n2, ldx2, D, ell, ell_len, sigma2, G, ldg, g_transposed, g_ell, g_sigma2,
                   gX2, workspace, workspace_bytes, S(stream));
+}
+int gpb_kern_bwd_mul(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                     const double* ell, int ell_len, const double* sigma2, const double* G, long ldg,
+                     int g_transposed, const double* Mul, long ldm, int symmetric, double* g_ell, double* g_sigma2,
+                     double* gX2, void* workspace, size_t workspace_bytes, void* stream) {
+  return kern_bwd_mul(kind, X, n1, ldx, X2, n2, ldx2, D, ell, ell_len, sigma2, G, ldg, g_transposed, Mul, ldm,
+                      symmetric, g_ell, g_sigma2, gX2, workspace, workspace_bytes, S(stream));
+}
+int gpb_kern_sop_fwd(int n_terms, const int* term_len, const int* leaf_kind, const double* const* leaf_ell,
+                     const int* leaf_ell_len, const double* const* leaf_sigma2, const double* X, int n1, long ldx,
+                     const double* X2, int n2, long ldx2, int D, const double* noise, int fill, double* K, long ldk,
+                     void* stream) {
+  return kern_sop_fwd(n_terms, term_len, leaf_kind, leaf_ell, leaf_ell_len, leaf_sigma2, X, n1, ldx, X2, n2, ldx2, D,
+                      noise, fill, K, ldk, S(stream));
 }
 int gpb_linear_kdiag(const double* X, int n, long ldx, int D, const double* v, double* out, void* stream) {
   return linear_kdiag(X, n, ldx, D, v, out, S(stream));

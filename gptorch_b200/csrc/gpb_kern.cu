@@ -10,52 +10,10 @@
 // upstream gradient against dK/d(length scales, variance, X2) in one pass over G, recomputing K on the fly.
 // For the GPR loss the upstream gradient W = 1/2 (dy Kinv - a a^T) is itself formed on the fly from the
 // blocked inverse left by gpb_potri_lower, so neither W nor K is ever materialised.
-#include "gpb_common.cuh"
+#include "gpb_kernfn.cuh"
 #include <algorithm>
 
 namespace gpb {
-
-enum { KERN_RBF = 0, KERN_EXP = 1, KERN_MATERN32 = 2, KERN_MATERN52 = 3, KERN_LINEAR = 4 };
-
-#define SQRT3 1.7320508075688772
-#define SQRT5 2.23606797749979
-
-// value of the kernel divided by the variance, as a function of the (clamped) scaled squared distance.
-__device__ __forceinline__ double kern_base(int kind, double r2) {
-  if (kind == KERN_RBF) return exp(-0.5 * r2);
-  const double r = sqrt(fmax(r2, 1e-40));  // gptorch/kernels.py:172
-  if (kind == KERN_EXP) return exp(-r);
-  if (kind == KERN_MATERN32) {
-    const double r3 = SQRT3 * r;
-    return (1.0 + r3) * exp(-r3);
-  }
-  const double r5 = SQRT5 * r;  // MATERN52
-  return (1.0 + r5 + (5.0 / 3.0) * r * r) * exp(-r5);
-}
-
-// kbase = K / sigma2 ; fac1 = fac / sigma2 where dK/d log(ell_d) = fac * delta_d^2 / ell_d^2.
-__device__ __forceinline__ void kern_base_fac(int kind, double r2, double& kbase, double& fac1) {
-  if (kind == KERN_RBF) {
-    kbase = exp(-0.5 * r2);
-    fac1 = kbase;
-    return;
-  }
-  const bool clamped = r2 < 1e-40;  // sqrt-clamp: zero gradient below the clamp (gptorch/kernels.py:171-172)
-  const double r = sqrt(fmax(r2, 1e-40));
-  if (kind == KERN_EXP) {
-    const double e = exp(-r);
-    kbase = e;
-    fac1 = clamped ? 0.0 : e / r;
-  } else if (kind == KERN_MATERN32) {
-    const double r3 = SQRT3 * r, e = exp(-r3);
-    kbase = (1.0 + r3) * e;
-    fac1 = clamped ? 0.0 : 3.0 * e;
-  } else {
-    const double r5 = SQRT5 * r, e = exp(-r5);
-    kbase = (1.0 + r5 + (5.0 / 3.0) * r * r) * e;
-    fac1 = clamped ? 0.0 : (5.0 / 3.0) * (1.0 + r5) * e;
-  }
-}
 
 // ================================================================================================
 // forward
@@ -212,7 +170,7 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
 int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
              const double* ell, int ell_len, const double* sigma2, const double* noise, int fill, double* K,
              long ldk, cudaStream_t stream) {
-  if (kind < 0 || kind > KERN_LINEAR) return GPB_ERR_BADARG;
+  if (kind < 0 || kind > KERN_PERIODIC) return GPB_ERR_BADARG;
   if (!X || !K || !ell || D <= 0 || (ell_len != 1 && ell_len != D)) return GPB_ERR_BADARG;
   if (kind != KERN_LINEAR && !sigma2) return GPB_ERR_BADARG;
   if (kind == KERN_LINEAR && ell_len != D) return GPB_ERR_BADARG;
@@ -286,6 +244,8 @@ struct KbwdParams {
   const double* ell; int ell_len;
   const double* sigma2;
   const double* G; long ldg; int g_trans;      // dense upstream gradient
+  const double* Mul; long ldm;                 // optional element-wise multiplier of G (same layout as G)
+  int symmetric;                               // X2 is X (only KERN_WHITE looks at it)
   const double* Kinv; long ldk; const double* kd; const double* a; int dy; long lda;  // GPR form
   int strips, nrc;
   double* part_h;    // [ncta][D + 2]: S_d ..., sum G*K/sigma2, tr W
@@ -408,11 +368,15 @@ __global__ void __launch_bounds__(KB_THREADS, 2) kern_bwd_kernel(const KbwdParam
           }
         } else if (valid) {
           g = p.g_trans ? p.G[static_cast<long>(j) * p.ldg + i] : __ldcs(&p.G[static_cast<long>(i) * p.ldg + j]);
+          if (p.Mul) g *= p.g_trans ? p.Mul[static_cast<long>(j) * p.ldm + i] : __ldcs(&p.Mul[static_cast<long>(i) * p.ldm + j]);
         }
         double h = 0.0;
         if (valid) {
           if (linear) {
             h = g;
+          } else if (p.kind >= KERN_CONSTANT) {
+            // Constant: K = sigma2; White: K = sigma2 [i == j] for K(X), 0 for K(X, X2) (gptorch/kernels.py:83-101)
+            if (dc == 0 && (p.kind == KERN_CONSTANT || (p.symmetric && i == j))) sK += g;
           } else {
             double kbase, fac1;
             kern_base_fac(p.kind, r2[rr], kbase, fac1);
@@ -566,11 +530,11 @@ static int kbwd_launch(KbwdParams& p, int ncb, double* g_ell, double* g_sigma2, 
   return GPB_OK;
 }
 
-int kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
-             const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
-             double* g_ell, double* g_sigma2, double* gX2, void* workspace, size_t workspace_bytes,
-             cudaStream_t stream) {
-  if (kind < 0 || kind > KERN_LINEAR) return GPB_ERR_BADARG;
+int kern_bwd_mul(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                 const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
+                 const double* Mul, long ldm, int symmetric, double* g_ell, double* g_sigma2, double* gX2,
+                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (kind < 0 || kind > KERN_WHITE) return GPB_ERR_BADARG;
   if (!X || !G || !ell || !g_ell || D <= 0 || (ell_len != 1 && ell_len != D)) return GPB_ERR_BADARG;
   if (kind != KERN_LINEAR && !sigma2) return GPB_ERR_BADARG;
   if (kind == KERN_LINEAR && ell_len != D) return GPB_ERR_BADARG;
@@ -583,12 +547,22 @@ int kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int 
   if (n1 <= 0 || p.n2 <= 0) return GPB_ERR_BADARG;
   p.D = D; p.ell = ell; p.ell_len = ell_len; p.sigma2 = sigma2;
   p.G = G; p.ldg = ldg; p.g_trans = g_transposed;
+  p.Mul = Mul; p.ldm = ldm; p.symmetric = (symmetric || !X2) ? 1 : 0;
   int ncb;
   kbwd_grid(n1, p.n2, false, ncb, p.nrc, p.strips);
   if (!workspace || workspace_bytes < kern_bwd_workspace_bytes(n1, p.n2, D)) return GPB_ERR_BADARG;
   p.part_h = static_cast<double*>(workspace);
   p.part_g2 = gX2 ? p.part_h + static_cast<size_t>(ncb) * p.strips * (D + 2) : nullptr;
   return kbwd_launch<false>(p, ncb, g_ell, g_sigma2, nullptr, gX2, stream);
+}
+
+int kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+             const double* ell, int ell_len, const double* sigma2, const double* G, long ldg, int g_transposed,
+             double* g_ell, double* g_sigma2, double* gX2, void* workspace, size_t workspace_bytes,
+             cudaStream_t stream) {
+  if (kind > KERN_PERIODIC) return GPB_ERR_BADARG;
+  return kern_bwd_mul(kind, X, n1, ldx, X2, n2, ldx2, D, ell, ell_len, sigma2, G, ldg, g_transposed, nullptr, 0, 0,
+                      g_ell, g_sigma2, gX2, workspace, workspace_bytes, stream);
 }
 
 size_t gpr_grad_workspace_bytes(int n, int D) {
@@ -601,7 +575,7 @@ int gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* el
              const double* sigma2, const double* Kinv, long ldk, const double* kdiag_blocks, const double* a,
              int dy, long lda_a, double* g_ell, double* g_sigma2, double* g_noise, void* workspace,
              size_t workspace_bytes, cudaStream_t stream) {
-  if (kind < 0 || kind > KERN_LINEAR) return GPB_ERR_BADARG;
+  if (kind < 0 || kind > KERN_PERIODIC) return GPB_ERR_BADARG;
   if (!X || !Kinv || !kdiag_blocks || !a || !ell || !g_ell || D <= 0 || n <= 0 || dy <= 0) return GPB_ERR_BADARG;
   if (ell_len != 1 && ell_len != D) return GPB_ERR_BADARG;
   if (kind != KERN_LINEAR && !sigma2) return GPB_ERR_BADARG;

@@ -1,8 +1,10 @@
 """Covariance functions with the reference's class names and call surface (gptorch/kernels.py).
 
-Stationary kernels (Rbf, Exp/Matern12, Matern32, Matern52) and Linear evaluate K through the fused CUDA
-kernel (one pass, analytic backward); Static kernels, Periodic and the Sum/Product combinators compose
-tensors like the reference does.
+Stationary kernels (Rbf, Exp/Matern12, Matern32, Matern52, Periodic) and Linear evaluate K through the fused CUDA
+kernel (one pass, analytic backward).  Sum / Product trees whose leaves are those kernels, Constant/Bias or White
+are rewritten as a sum of products of leaves and evaluated by ONE pass of the composite kernel
+(gpb_kern_sop_fwd) instead of one N x N tensor per child; trees with user-defined leaves, or larger
+than the native limits, compose tensors like the reference does.
 """
 import numpy as np
 import torch
@@ -148,10 +150,8 @@ SquaredExponential = Rbf
 
 
 class Periodic(Stationary):
-    """variance * cos(r)  (gptorch/kernels.py:228-235); composite torch ops."""
-
-    def K(self, X, X2=None):
-        return self.variance.transform() * torch.cos(self.dist(X, X2))
+    """variance * cos(r)  (gptorch/kernels.py:228-235)"""
+    _kind = nv.KIND["Periodic"]
 
 
 class Linear(Kernel):
@@ -181,17 +181,88 @@ class Combination(Kernel):
         self.kern2 = kern2
 
 
-class Product(Combination):
+def _leaf_kind(kernel):
+    """Native family index of a leaf the composite kernel can evaluate, or None (a subclass that overrides K() is
+    user code and is composed through its own K)."""
+    cls = type(kernel)
+    if isinstance(kernel, Stationary):
+        return kernel._kind if (kernel._kind is not None and cls.K is Stationary.K) else None
+    if isinstance(kernel, Linear):
+        return nv.KERN_LINEAR if cls.K is Linear.K else None
+    if isinstance(kernel, Constant):
+        return nv.KERN_CONSTANT if cls.K is Constant.K else None
+    if isinstance(kernel, White):
+        return nv.KERN_WHITE if cls.K is White.K else None
+    return None
+
+
+def sum_of_products(kernel):
+    """The kernel as a list of terms, each a list of leaf kernels, such that K = sum_t prod_{l in t} k_l -- or None
+    when a leaf is not a native family or the expansion exceeds the composite kernel's limits."""
+    if isinstance(kernel, Combination):
+        a, b = sum_of_products(kernel.kern1), sum_of_products(kernel.kern2)
+        if a is None or b is None:
+            return None
+        terms = a + b if isinstance(kernel, Sum) else [ta + tb for ta in a for tb in b]
+        if not isinstance(kernel, (Sum, Product)) or type(kernel).K not in (Sum.K, Product.K):
+            return None
+        if len(terms) > nv.SOP_MAX_TERMS or sum(len(t) for t in terms) > nv.SOP_MAX_LEAVES:
+            return None
+        return terms
+    return [[kernel]] if _leaf_kind(kernel) is not None else None
+
+
+def composite_spec(terms):
+    """(spec, params) for the composite autograd nodes: spec mirrors `terms` with (kind, ell index, sigma2 index)
+    into the de-duplicated list of transformed parameter tensors."""
+    params, index = [], {}
+
+    def slot(param):
+        key = id(param)
+        if key not in index:
+            index[key] = len(params)
+            params.append(param.transform())
+        return index[key]
+
+    spec = []
+    for term in terms:
+        row = []
+        for leaf in term:
+            kind = _leaf_kind(leaf)
+            if kind == nv.KERN_LINEAR:
+                row.append((kind, slot(leaf.variance), -1))
+            elif kind >= nv.KERN_CONSTANT:
+                row.append((kind, -1, slot(leaf.variance)))
+            else:
+                row.append((kind, slot(leaf.length_scales), slot(leaf.variance)))
+        spec.append(tuple(row))
+    return tuple(spec), params
+
+
+class _Fusable(Combination):
+    """Sum / Product: one fused pass when every leaf is native, the reference's tensor composition otherwise."""
+
     def K(self, X, X2=None):
-        return self.kern1.K(X, X2) * self.kern2.K(X, X2)
+        terms = sum_of_products(self)
+        if terms is None:
+            return self._compose(self.kern1.K(X, X2), self.kern2.K(X, X2))
+        spec, params = composite_spec(terms)
+        return ag.CompositeKernelFn.apply(spec, _f64(X), None if X2 is None else _f64(X2), None, *params)
+
+
+class Product(_Fusable):
+    @staticmethod
+    def _compose(a, b):
+        return a * b
 
     def Kdiag(self, X):
         return self.kern1.Kdiag(X) * self.kern2.Kdiag(X)
 
 
-class Sum(Combination):
-    def K(self, X, X2=None):
-        return self.kern1.K(X, X2) + self.kern2.K(X, X2)
+class Sum(_Fusable):
+    @staticmethod
+    def _compose(a, b):
+        return a + b
 
     def Kdiag(self, X):
         return self.kern1.Kdiag(X) + self.kern2.Kdiag(X)

@@ -26,8 +26,9 @@ class GPR(GPModel):
         """log p(y | x, theta), shape [1] (Rasmussen & Williams alg. 2.1; gptorch/models/gpr.py:47-67).
 
         With a stationary kernel and the Gaussian likelihood the whole evaluation is one fused native node
-        (covariance build -> Cholesky -> solve -> log-det, analytic backward).  Other kernels (Sum, Product,
-        Linear, ...) go through the reference's step-by-step form on the native primitives.
+        (covariance build -> Cholesky -> solve -> log-det, analytic backward); Sum / Product trees of native leaves
+        (and a bare Linear) use the composite form of the same node.  Kernels with user-defined leaves go through the
+        reference's step-by-step form on the native primitives.
         """
         x = x if x is not None else self.X
         y = y if y is not None else self.Y
@@ -39,6 +40,11 @@ class GPR(GPModel):
         if kind is not None and isinstance(self.likelihood, Gaussian):
             return ag.GPRLogLikFn.apply(kind, x, resid, self.kernel.length_scales.transform(),
                                         self.kernel.variance.transform(), self.likelihood.variance.transform())
+        terms = kernels.sum_of_products(self.kernel) if isinstance(self.likelihood, Gaussian) else None
+        if terms is not None:
+            spec, params = kernels.composite_spec(terms)
+            return ag.GPRCompositeLogLikFn.apply(spec, x.to(torch.float64), resid, self.likelihood.variance.transform(),
+                                                 *params)
         L = cholesky(self._compute_kyy(x=x))
         alpha = trtrs(resid, L)
         red_logdet = ag.LogDetFn.apply(L)
@@ -53,6 +59,10 @@ class GPR(GPModel):
         if kind is not None:
             return ag.KernelFn.apply(kind, x.to(torch.float64), None, self.kernel.length_scales.transform(),
                                      self.kernel.variance.transform(), noise)
+        terms = kernels.sum_of_products(self.kernel)
+        if terms is not None:
+            spec, params = kernels.composite_spec(terms)
+            return ag.CompositeKernelFn.apply(spec, x.to(torch.float64), None, noise, *params)
         n = x.shape[0]
         return self.kernel.K(x) + noise * torch.eye(n, dtype=x.dtype, device=x.device)
 

@@ -38,7 +38,11 @@ enum gpb_kernel_kind {
   GPB_KERN_EXP = 1,      /* == Matern12 */
   GPB_KERN_MATERN32 = 2,
   GPB_KERN_MATERN52 = 3,
-  GPB_KERN_LINEAR = 4
+  GPB_KERN_LINEAR = 4,
+  GPB_KERN_PERIODIC = 5, /* variance * cos(r), gptorch/kernels.py:228-235 */
+  /* leaves of composite kernels only (gpb_kern_sop_fwd, gpb_kern_bwd_mul): gptorch/kernels.py:83-101 */
+  GPB_KERN_CONSTANT = 6,
+  GPB_KERN_WHITE = 7
 };
 
 /* Which part of a symmetric output to produce. */
@@ -82,6 +86,28 @@ int gpb_kern_bwd(int kind, const double* X, int n1, long ldx, const double* X2, 
                  const double* ell, int ell_len, const double* sigma2, const double* G, long ldg,
                  int g_transposed, double* g_ell, double* g_sigma2, double* gX2, void* workspace,
                  size_t workspace_bytes, void* stream);
+
+/* gpb_kern_bwd with an optional element-wise multiplier: the upstream gradient is G .* Mul (Mul: same shape, layout
+ * and transposition flag as G; NULL = ones).  This is the backward of one leaf of a Product kernel
+ * (gptorch/kernels.py:286-295: d(k1 k2)/d theta1 = k2 dk1/d theta1), with Mul = the product of the other leaves.
+ * Also accepts GPB_KERN_CONSTANT and GPB_KERN_WHITE (only g_sigma2 is meaningful; `ell` may be any valid vector of
+ * length ell_len).  `symmetric` != 0 declares X2 == X even when X2 is passed explicitly (White is the identity then). */
+int gpb_kern_bwd_mul(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
+                     const double* ell, int ell_len, const double* sigma2, const double* G, long ldg,
+                     int g_transposed, const double* Mul, long ldm, int symmetric, double* g_ell, double* g_sigma2,
+                     double* gX2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Composite covariance in one pass: K = sum_t prod_{l in term t} k_l(X, X2) [+ noise I when X2 == NULL].
+ * Replaces the Sum / Product combinators (gptorch/kernels.py:286-306) over leaf kernels of any family above --
+ * every tree of + and * is a sum of products of leaves -- without the reference's N x N temporary per child.
+ *   n_terms <= 8 terms; term t has term_len[t] consecutive leaves (<= 16 leaves in total); all arrays below are
+ *   HOST arrays indexed by leaf:  leaf_kind, leaf_ell (device pointers; Linear: the variance vector; ignored for
+ *   Constant / White), leaf_ell_len (1 or D), leaf_sigma2 (device pointers; ignored for Linear).
+ *   noise / fill / K / ldk as in gpb_kern_fwd. */
+int gpb_kern_sop_fwd(int n_terms, const int* term_len, const int* leaf_kind, const double* const* leaf_ell,
+                     const int* leaf_ell_len, const double* const* leaf_sigma2, const double* X, int n1, long ldx,
+                     const double* X2, int n2, long ldx2, int D, const double* noise, int fill, double* K, long ldk,
+                     void* stream);
 
 /* Kdiag for the non-stationary kernel (Linear.Kdiag, gptorch/kernels.py:264-265): out[i] = sum_d v_d x_id^2.
  * Stationary kernels return the variance broadcast (gptorch/kernels.py:174-179) and need no kernel. */

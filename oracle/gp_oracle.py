@@ -108,7 +108,25 @@ def cov(kind, X, X2, ell, variance):
         return variance * (1.0 + s5 * r + 5.0 / 3.0 * r * r) * torch.exp(-s5 * r)
     if kind == "Linear":
         return torch.mm(X * variance, (X if X2 is None else X2).t())
+    if kind == "Periodic":      # gptorch/kernels.py:228-235
+        return variance * torch.cos(scaled_r(X, X2, ell))
+    if kind in ("Constant", "Bias"):   # gptorch/kernels.py:96-101
+        n1, n2 = X.size(0), (X if X2 is None else X2).size(0)
+        return variance.expand(n1, n2)
+    if kind == "White":         # gptorch/kernels.py:83-93
+        if X2 is None:
+            return variance.expand(X.size(0)).diag()
+        return torch.zeros(X.size(0), X2.size(0), dtype=DTYPE)
     raise ValueError(kind)
+
+
+def cov_composite(expr, leaves, X, X2=None):
+    """Sum / Product trees (gptorch/kernels.py:286-306).  `expr` is a Python expression over k0, k1, ... using + and *
+    (the reference builds the same tree through Kernel.__add__/__mul__, gptorch/kernels.py:36-40); leaves[i] is
+    (kind, ell or None, variance) with tensors.  K of a Sum / Product is the element-wise sum / product of the
+    children's K, so the expression is evaluated on the leaf matrices."""
+    env = {"k%d" % i: cov(kind, X, X2, ell, var) for i, (kind, ell, var) in enumerate(leaves)}
+    return eval(expr, {"__builtins__": {}}, env)  # noqa: S307 (test infrastructure; fixed expressions)
 
 
 def cov_diag(kind, X, variance):

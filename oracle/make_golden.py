@@ -238,6 +238,96 @@ def svgp_case(kind, n, d, m, dy, which, batch=None, n_test=0):
     return case
 
 
+COMPOSITES = [
+    # (name, expression over k0.., leaf kinds)
+    ("lin_rbf_const", "k0 + k1 + k2", ["Linear", "Rbf", "Constant"]),          # examples/regression_1d.py:42
+    ("rbf_x_matern32", "k0 * k1", ["Rbf", "Matern32"]),
+    ("mixed_tree", "(k0 + k1) * k2 + k3", ["Rbf", "Linear", "Periodic", "White"]),
+    ("periodic_only", "k0 + k1", ["Periodic", "White"]),
+    ("exp_x_const_plus_m52", "k0 * k1 + k2", ["Matern52", "Constant", "Exp"]),
+]
+
+
+def _leaf_values(kinds, d):
+    vals = []
+    for i, kind in enumerate(kinds):
+        var = 0.7 + 0.4 * i
+        if kind == "Linear":
+            vals.append((kind, None, var * (0.5 + 0.25 * np.arange(d))))
+        elif kind in ("Constant", "White"):
+            vals.append((kind, None, np.array([0.3 + 0.2 * i])))
+        else:
+            vals.append((kind, 0.6 + 0.3 * np.arange(d) + 0.1 * i, np.array([var])))
+    return vals
+
+
+def composite_case(name, expr, kinds, n=90, d=3, n2=11):
+    """One composite kernel through the real reference: K(X), K(X, X2), GPR loss + gradients, GPR prediction."""
+    X, Y, g = O.synth_regression(n, d)
+    X2 = torch.rand(n2, d, generator=g, dtype=torch.float64)
+    vals = _leaf_values(kinds, d)
+    ref_cls = {"Linear": rk.Linear, "Rbf": rk.Rbf, "Constant": rk.Constant, "White": rk.White, "Periodic": rk.Periodic,
+               "Matern32": rk.Matern32, "Matern52": rk.Matern52, "Exp": rk.Exp}
+    leaves = []
+    for kind, ell, var in vals:
+        if kind == "Linear":
+            leaves.append(ref_cls[kind](d, variance=var.copy(), ARD=True))
+        elif kind in ("Constant", "White"):
+            leaves.append(ref_cls[kind](d, variance=float(var[0])))
+        else:
+            leaves.append(ref_cls[kind](d, ARD=True, length_scales=ell.copy(), variance=float(var[0])))
+    kern = eval(expr, {"__builtins__": {}}, {"k%d" % i: k for i, k in enumerate(leaves)})
+    noise = 0.05
+    with torch.no_grad():
+        Kx, Kx2 = kern.K(X).numpy(), kern.K(X, X2).numpy()
+    model = GPR(X.numpy(), Y.numpy(), kern, likelihood=rl.Gaussian(variance=noise))
+    loss = model.loss()
+    loss.backward()
+    case = {"expr": expr, "kinds": np.array(kinds), "n": n, "d": d, "X": X.numpy(), "Y": Y.numpy(), "X2": X2.numpy(),
+            "noise": noise, "Kx": Kx, "Kx2": Kx2, "loss": loss.detach().numpy(),
+            "g_noise": model.likelihood.variance.grad.numpy().copy()}
+    # oracle on the same tree, raw (log) parameters as leaves of autograd
+    raws, o_leaves = [], []
+    for kind, ell, var in vals:
+        r_ell = torch.log(T(ell)).requires_grad_(True) if ell is not None else None
+        r_var = torch.log(T(var)).requires_grad_(True)
+        raws.append((r_ell, r_var))
+        o_leaves.append((kind, None if r_ell is None else r_ell.exp(), r_var.exp()))
+    r_noise = torch.log(T([noise])).requires_grad_(True)
+    check("composite Kx", O.cov_composite(expr, o_leaves, X).detach().numpy(), Kx)
+    check("composite Kx2", O.cov_composite(expr, o_leaves, X, X2).detach().numpy(), Kx2)
+    Ky = O.cov_composite(expr, o_leaves, X) + r_noise.exp() * torch.eye(n, dtype=torch.float64)
+    L = O.chol(Ky)
+    alpha = O.tri_solve(Y, L)
+    o_loss = 0.5 * alpha.pow(2).sum() + O.tri_logdet(L) + 0.5 * n * np.log(2 * np.pi)
+    o_loss.backward()
+    check("composite loss", o_loss.detach().numpy(), loss.detach().numpy())
+    check("composite g_noise", r_noise.grad.numpy(), case["g_noise"], 1e-10)
+    for i, (leaf, (r_ell, r_var)) in enumerate(zip(leaves, raws)):
+        case["leaf%d/variance" % i] = vals[i][2]
+        case["leaf%d/g_variance" % i] = leaf.variance.grad.numpy().copy()
+        check("composite g_var %d" % i, r_var.grad.numpy(), leaf.variance.grad.numpy(), 1e-10)
+        if r_ell is not None:
+            case["leaf%d/ell" % i] = vals[i][1]
+            case["leaf%d/g_length_scales" % i] = leaf.length_scales.grad.numpy().copy()
+            check("composite g_ell %d" % i, r_ell.grad.numpy(), leaf.length_scales.grad.numpy(), 1e-10)
+    Xs = torch.rand(6, d, generator=g, dtype=torch.float64)
+    with torch.no_grad():
+        mu, var_d = model._predict(Xs, diag=True)
+    case.update({"Xs": Xs.numpy(), "pred_mean": mu.numpy(), "pred_var": var_d.numpy().copy()})
+    return case
+
+
+def composite_cases():
+    out, names = {}, []
+    for name, expr, kinds in COMPOSITES:
+        flatten(name, composite_case(name, expr, kinds), out)
+        names.append(name)
+        print("composite", name, "loss", out[name + "/loss"])
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "composite_cases.npz"), **out)
+
+
 def flatten(prefix, case, out):
     for k, v in case.items():
         out["%s/%s" % (prefix, k)] = np.asarray(v)
@@ -245,6 +335,10 @@ def flatten(prefix, case, out):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--composite-only" in sys.argv:      # add / refresh tests/golden/composite_cases.npz without touching the rest
+        composite_cases()
+        return
+    composite_cases()
     fx = reference_fixtures()
     np.savez_compressed(os.path.join(OUT, "reference_fixtures.npz"), **fx)
 

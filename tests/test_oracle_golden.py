@@ -141,3 +141,32 @@ def test_svgp_oracle_reproduces_reference_run(name):
     assert rel_err(loss.item(), c.get(name, "loss")) <= 1e-13
     assert rel_err(qm.grad.numpy(), c.get(name, "g_q_mu")) <= 1e-10
     assert rel_err(Zp.grad.numpy(), c.get(name, "g_Z")) <= 1e-10
+
+
+_COMP = Cases("composite_cases.npz")
+
+
+def _composite_leaves(c, name):
+    kinds = [str(k) for k in c.get(name, "kinds")]
+    leaves = []
+    for i, kind in enumerate(kinds):
+        ell = c.get(name, "leaf%d/ell" % i)
+        leaves.append((kind, None if ell is None else T(ell), T(c.get(name, "leaf%d/variance" % i))))
+    return kinds, leaves
+
+
+@pytest.mark.parametrize("name", _COMP.names)
+def test_composite_kernels_match_reference(name):
+    """Sum / Product trees over Linear, stationary, Periodic, Constant and White leaves
+    (gptorch/kernels.py:83-101, 228-306) against K(X), K(X, X2) and the GPR loss of the real reference."""
+    c = _COMP
+    _, leaves = _composite_leaves(c, name)
+    expr = str(c.get(name, "expr"))
+    X, X2, Y = T(c.get(name, "X")), T(c.get(name, "X2")), T(c.get(name, "Y"))
+    assert rel_err(O.cov_composite(expr, leaves, X).numpy(), c.get(name, "Kx")) < 1e-13
+    assert rel_err(O.cov_composite(expr, leaves, X, X2).numpy(), c.get(name, "Kx2")) < 1e-13
+    n = X.shape[0]
+    L = O.chol(O.cov_composite(expr, leaves, X) + float(c.get(name, "noise")) * torch.eye(n, dtype=torch.float64))
+    alpha = O.tri_solve(Y, L)
+    loss = 0.5 * alpha.pow(2).sum() + O.tri_logdet(L) + 0.5 * n * np.log(2 * np.pi)
+    assert rel_err(loss.numpy(), c.get(name, "loss")) < 1e-12
