@@ -163,7 +163,7 @@ class CholeskyFn(Function):
         n = A.shape[0]
         buf, ld = nv.sym_buffer_from(A)
         dinv, info = nv.potrf_(buf, ld)
-        status = int(info.item())  # the one host sync of a factorisation (SURVEY 7 "hard parts")
+        status = nv.read_info(info)  # the one host sync of a factorisation (SURVEY 7 "hard parts")
         if status != 0:
             _raise_not_pd(status)
         nv.tri_zero_upper_(buf, ld)
@@ -336,7 +336,7 @@ class GPRLogLikFn(Function):
                 nv.add_diag_(buf, ld, 10.0 ** (-JITTER_TRIES + attempt - 1))
             with nv.phase("potrf"):
                 dinv, info = nv.potrf_(buf, ld)
-            if int(info.item()) == 0:
+            if nv.read_info(info) == 0:
                 break
         else:
             raise RuntimeError("Max tries exceeded.")
@@ -391,7 +391,7 @@ class GPRCompositeLogLikFn(Function):
                 nv.add_diag_(buf, ld, 10.0 ** (-JITTER_TRIES + attempt - 1))
             with nv.phase("potrf"):
                 dinv, info = nv.potrf_(buf, ld)
-            if int(info.item()) == 0:
+            if nv.read_info(info) == 0:
                 break
         else:
             raise RuntimeError("Max tries exceeded.")

@@ -54,6 +54,38 @@ class phase:
         return False
 
 
+# ---------------------------------------------------------------------------------------------- factorisation status
+_deferred_info = None   # device int32 [1]: max of the LAPACK-style `info` values seen while host reads are deferred
+
+
+def read_info(info):
+    """Status of a factorisation: normally ONE host read of the device int (the only sync of an evaluation).  While
+    an evaluation is being captured into / replayed from a CUDA graph (gptorch_b200/model.py GraphedEvaluation) the
+    host cannot read: the value is folded into a device accumulator that the replay returns with the loss, and the
+    caller proceeds as if the factorisation had succeeded."""
+    if _deferred_info is not None:
+        torch.maximum(_deferred_info, info.reshape(-1)[:1], out=_deferred_info)
+        return 0
+    return int(info.item())
+
+
+class deferred_info:
+    """Context manager: route read_info() into `accumulator` (device int32 [1])."""
+
+    def __init__(self, accumulator):
+        self.acc = accumulator
+
+    def __enter__(self):
+        global _deferred_info
+        self.prev, _deferred_info = _deferred_info, self.acc
+        return self.acc
+
+    def __exit__(self, *exc):
+        global _deferred_info
+        _deferred_info = self.prev
+        return False
+
+
 def launch_count():
     return _lib.load().gpb_launch_count()
 

@@ -228,3 +228,10 @@ class GPModel(Model):
 
     def _loss(self, *args, **kwargs):
         return -(self.log_likelihood(*args, **kwargs) + self.log_prior())
+
+    def _graphable(self):
+        """Full-batch evaluations on one GPU are static device work (Model._loss_and_grad replays them as a CUDA
+        graph); minibatch models draw indices on the host every step, and row-sharded models call NCCL."""
+        from .. import settings
+        return (self.X.is_cuda and self.X.shape[0] <= settings.graph_max_rows and getattr(self, "batch_size", None) is None
+                and getattr(self, "_group", None) is None)

@@ -396,3 +396,85 @@ def test_distributed_gpr_loss_and_gradient(n, panel):
         errs = ret[rank]
         assert errs[0] <= LML_TOL and errs[-1] <= 1e-13
         assert max(errs[1:-1]) <= GRAD_TOL
+
+
+# ----------------------------------------------------------------------------------------------------------
+# optimiser bridge: CUDA-graph replay of loss() + backward()  (gptorch_b200/model.py GraphedEvaluation)
+# ----------------------------------------------------------------------------------------------------------
+def _bridge_model(family, n=160):
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import GPR, VFE
+    X, Y, g = O.synth_regression(n, 2)
+    if family == "GPR-composite":
+        return GPR(X.numpy(), Y.numpy(), kernels.Linear(2) + kernels.Rbf(2) + kernels.Constant(2))
+    if family == "GPR":
+        return GPR(X.numpy(), Y.numpy(), kernels.Matern32(2, ARD=True), likelihood=likelihoods.Gaussian(variance=0.05))
+    return VFE(X.numpy(), Y.numpy(), kernels.Rbf(2, ARD=True), inducing_points=O.synth_inducing(X, 12, g).numpy(),
+               likelihood=likelihoods.Gaussian(variance=0.05))
+
+
+@pytest.mark.parametrize("family", ["GPR-composite", "GPR", "VFE"])
+def test_graphed_optimizer_bridge_matches_eager(family, capsys):
+    """Model._loss_and_grad replays a captured CUDA graph; values and gradients must equal the eager evaluation bit
+    for bit (same kernels, same order), for every parameter vector, and the Params must hold the new values."""
+    from gptorch_b200 import settings
+    rng = np.random.RandomState(3)
+    graphed, eager = _bridge_model(family), _bridge_model(family)
+    theta0 = graphed._get_param_array()
+    assert graphed._graphable()
+    for k in range(4):
+        theta = theta0 + 0.2 * k * rng.randn(theta0.size)
+        settings.cuda_graphs = True
+        try:
+            f1, g1 = graphed._loss_and_grad(theta)
+        finally:
+            settings.cuda_graphs = False
+        try:
+            f2, g2 = eager._loss_and_grad(theta)
+        finally:
+            settings.cuda_graphs = True
+        assert "_graph_eval" in graphed.__dict__ and "_graph_eval" not in eager.__dict__
+        assert f1 == f2 and np.array_equal(g1, g2)
+        assert np.array_equal(graphed._get_param_array(), theta)
+    capsys.readouterr()
+
+
+def test_graphed_bridge_falls_back_for_jitter_and_uncapturable_models(capsys):
+    """(1) Ky not positive-definite without jitter: the replay reports the failed factorisation and the evaluation is
+    redone eagerly with the reference's jitter schedule.  (2) A model whose loss() reads the device from the host
+    cannot be captured: a warning, then eager evaluation."""
+    import warnings
+    from gptorch_b200 import kernels, likelihoods, settings
+    from gptorch_b200.models import GPR
+    x = np.linspace(0, 1, 40).reshape(-1, 1)
+    x = np.concatenate([x, x])                         # duplicated points: K is singular
+    y = np.sin(6 * x)
+    mk = lambda: GPR(x, y, kernels.Rbf(1), likelihood=likelihoods.Gaussian(variance=1e-30))  # noqa: E731
+    a, b = mk(), mk()
+    theta = a._get_param_array()
+    f1, g1 = a._loss_and_grad(theta)
+    settings.cuda_graphs = False
+    try:
+        f2, g2 = b._loss_and_grad(theta)
+    finally:
+        settings.cuda_graphs = True
+    assert np.isfinite(f1) and f1 == f2 and np.array_equal(g1, g2)
+
+    class HostRead(torch.nn.Module):
+        def forward(self, x):
+            return torch.zeros(x.shape[0], 1, dtype=torch.float64, device=x.device) + float(x.sum().item()) * 0.0
+
+    m = GPR(x[:40], y[:40], kernels.Rbf(1), mean_function=HostRead(), likelihood=likelihoods.Gaussian(variance=0.1))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        f, g = m._loss_and_grad(m._get_param_array())
+    assert any("CUDA-graph capture" in str(x.message) for x in w)
+    assert m.__dict__.get("_graph_state") == "failed" and np.isfinite(f) and np.all(np.isfinite(g))
+    f_again, _ = m._loss_and_grad(m._get_param_array())      # stays on the eager path, still works
+    assert f_again == f
+    # the GPU is still healthy for other models after the failed capture
+    ok = _bridge_model("GPR")
+    fo, go = ok._loss_and_grad(ok._get_param_array())
+    assert np.isfinite(fo) and "_graph_eval" in ok.__dict__
+    capsys.readouterr()
