@@ -23,3 +23,9 @@ if what == "all":
     nv.gpr_grad(0, X, ell, s2, buf, ld, kd, a)
 torch.cuda.synchronize()
 print("info", info.item())
+if what == "all":
+    # composite kernel (Linear + Rbf + Constant, BASELINE config #1's kernel) in one pass at the same N
+    v = torch.ones(8, dtype=torch.float64, device=dev); c = torch.ones(1, dtype=torch.float64, device=dev)
+    out, ldo = nv._aligned_empty(n, n, dev)
+    nv.kern_sop_fwd([[(4, v, None)], [(0, ell, s2)], [(6, None, c)]], X, None, noise=noise, lower=True, out=out, ldk=ldo)
+    torch.cuda.synchronize()
