@@ -201,11 +201,20 @@ def dominant_launch_probe():
             "ms": ms, "flop": flop, "tflops": flop / ms / 1e9}
 
 
+def synth_regression(n, d, seed=1234):
+    """SURVEY 8d's synthetic inputs (CPU generator, so the reference's loss pins apply): X ~ U[0,1)^d,
+    Y = sin(X w) + 0.1 eps.  Stated here rather than imported: oracle/ is only the checker / CPU baseline."""
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(n, d, generator=g, dtype=torch.float64)
+    w = torch.randn(d, 1, generator=g, dtype=torch.float64)
+    Y = torch.sin(X @ w) + 0.1 * torch.randn(n, 1, generator=g, dtype=torch.float64)
+    return X, Y, g
+
+
 def build_model(n, device):
-    from oracle import gp_oracle as O   # input generator only (shared with the oracle so the loss pins apply)
     from gptorch_b200 import kernels, likelihoods
     from gptorch_b200.models import GPR
-    X, Y, _ = O.synth_regression(n, D_IN)
+    X, Y, _ = synth_regression(n, D_IN)
     model = GPR(X.numpy(), Y.numpy(), kernels.Rbf(D_IN, ARD=True), likelihood=likelihoods.Gaussian(variance=0.01))
     return model, X, Y
 

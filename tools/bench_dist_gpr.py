@@ -23,10 +23,10 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
     os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    from oracle import gp_oracle as O
+    from bench import synth_regression
     from gptorch_b200 import kernels, likelihoods
     from gptorch_b200.models import GPR, DistributedGPR
-    X, Y, _ = O.synth_regression(args.n, args.d)
+    X, Y, _ = synth_regression(args.n, args.d)
     model = DistributedGPR(X.numpy(), Y.numpy(), kernels.Rbf(args.d, ARD=True), likelihood=likelihoods.Gaussian(variance=0.01),
                            panel=args.panel)
     params = [p for p in model.parameters() if p.requires_grad]
