@@ -251,3 +251,51 @@ def test_composite_falls_back_for_user_kernels():
     assert kernels.sum_of_products(k) is None
     x = torch.rand(9, 2, dtype=torch.float64).cuda()
     assert torch.allclose(k.K(x), 3.0 * kernels.Rbf(2).K(x))
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (5, 3), (129, 257), (300, 64)])
+def test_composite_kernel_ragged_shapes_and_fill(n1, n2):
+    """gpb_kern_sop_fwd on ragged / tiny shapes, the lower-only fill with the noise diagonal, and empty inputs."""
+    from oracle import gp_oracle as O
+    from gptorch_b200 import _native as nv
+    d = 4
+    g = torch.Generator().manual_seed(n1 * 1000 + n2)
+    X = torch.rand(n1, d, generator=g, dtype=torch.float64)
+    X2 = torch.rand(n2, d, generator=g, dtype=torch.float64)
+    ell = torch.tensor([0.5, 0.8, 1.1, 1.4], dtype=torch.float64)
+    one, two = torch.tensor([1.3], dtype=torch.float64), torch.tensor([0.4], dtype=torch.float64)
+    v = torch.tensor([0.2, 0.3, 0.4, 0.5], dtype=torch.float64)
+    leaves = [("Matern52", ell, one), ("Linear", None, v), ("Periodic", ell[:1], two), ("White", None, two)]
+    expr = "k0 * k1 + k2 + k3"
+    c = lambda t: None if t is None else t.cuda()  # noqa: E731
+    terms = [[(nv.KIND["Matern52"], c(ell), c(one)), (nv.KIND["Linear"], c(v), None)],
+             [(nv.KIND["Periodic"], c(ell[:1]), c(two))], [(nv.KIND["White"], None, c(two))]]
+    want = O.cov_composite(expr, leaves, X, X2).numpy()
+    got = nv.kern_sop_fwd(terms, X.cuda(), X2.cuda()).cpu().numpy()
+    assert got.shape == (n1, n2) and rel_err(got, want) < 1e-12
+    # symmetric: noise on the diagonal, lower fill leaves the strictly-upper 128-column tiles untouched
+    noise = torch.tensor([0.07], dtype=torch.float64)
+    want = (O.cov_composite(expr, leaves, X) + 0.07 * torch.eye(n1, dtype=torch.float64)).numpy()
+    full = nv.kern_sop_fwd(terms, X.cuda(), None, noise=noise.cuda()).cpu().numpy()
+    assert rel_err(full, want) < 1e-12
+    buf, ld = nv._aligned_empty(n1, n1, torch.device("cuda"))
+    buf.fill_(-7.0)
+    low = nv.kern_sop_fwd(terms, X.cuda(), None, noise=noise.cuda(), lower=True, out=buf, ldk=ld).cpu().numpy()
+    assert rel_err(np.tril(low), np.tril(want)) < 1e-12
+    # empty second argument
+    assert nv.kern_sop_fwd(terms, X.cuda(), X2[:0].cuda()).shape == (n1, 0)
+
+
+def test_composite_kernel_limits():
+    """More than 8 terms / 16 leaf evaluations: the tree is composed from tensors instead (same numbers)."""
+    from gptorch_b200 import kernels, _native as nv
+    x = torch.rand(33, 2, dtype=torch.float64).cuda()
+    leaves = [kernels.Rbf(2, variance=0.1 * (i + 1)) for i in range(9)]
+    k = leaves[0]
+    for leaf in leaves[1:]:
+        k = k + leaf
+    assert kernels.sum_of_products(k) is None
+    ref = sum(leaf.K(x) for leaf in leaves)
+    assert torch.allclose(k.K(x), ref, rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):
+        nv.kern_sop_fwd([[(0, torch.ones(1).double().cuda(), torch.ones(1).double().cuda())]] * 9, x, None)
