@@ -63,11 +63,25 @@ def cpu_eval_seconds(n, repeats=1):
     return best
 
 
+def default_cpu_sample(cores):
+    """Sample size of the CPU leg: about 10-30 s of host work per evaluation (the reference path costs
+    ~4.3 N^3 flop and ~9 N^2 fp64 temporaries), bounded by the host's free memory."""
+    n = 12288 if cores >= 16 else (8192 if cores >= 8 else 4096)
+    try:
+        import psutil
+        free = psutil.virtual_memory().available
+        while n > 4096 and 16 * 8 * n * n > free:
+            n -= 4096
+    except Exception:
+        n = min(n, 8192)
+    return n
+
+
 def cpu_baseline(n_full, sample_n=0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     if not sample_n:
-        sample_n = 8192 if cores >= 32 else 4096
+        sample_n = default_cpu_sample(cores)
     sample_n = min(sample_n, n_full)
     cpu_eval_seconds(1024)  # warm up MKL / autograd
     sec = cpu_eval_seconds(sample_n)
@@ -88,7 +102,7 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_n = args.cpu_sample_n or (8192 if cores >= 32 else 4096)
+    sample_n = args.cpu_sample_n or default_cpu_sample(cores)
     sample_n = min(sample_n, args.n)
     for _ in range(max(args.warmup, 1)):
         cpu_eval_seconds(1024)
