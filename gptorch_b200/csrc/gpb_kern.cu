@@ -41,6 +41,9 @@ struct KfwdParams {
 
 // 64 x 128 tile per CTA, 8 warps (2 x 4) of 32 x 32: 32 fp64 accumulators per thread keeps the kernel at two CTAs
 // (16 warps) per SM, which is what hides the latency of the exp() chains in the epilogue.
+// KIND is a compile-time constant: the family switch inside kern_base() folds away, and the polynomial constants of
+// the one exp() that remains are shared by the 32 unrolled elements instead of being re-materialised per branch.
+template <int KIND>
 __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParams p) {
   __shared__ double As[KF_TM * KF_LD];
   __shared__ double Bs[KF_TN * KF_LD];
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 1, wn = warp >> 1;
   const int r = lane >> 2, kk = lane & 3;
-  const bool linear = p.kind == KERN_LINEAR;
+  constexpr bool linear = KIND == KERN_LINEAR;
 
   double acc[KF_MI][KF_NI][2];
 #pragma unroll
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
           // K(X) diagonal: the reference's expansion leaves O(1e-16) round-off here, which sqrt() turns into
           // O(1e-8) noise for Exp/Matern; the distance of a point to itself is exactly 0.
           if (p.symmetric && row == col + e) r2 = 0.0;
-          v[e] = sig2 * kern_base(p.kind, r2);
+          v[e] = sig2 * kern_base(KIND, r2);
         }
         if (p.symmetric && row == col + e) v[e] += noise;
       }
@@ -195,7 +198,14 @@ int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int 
     const int q = tiles_m / 2;               // complete pairs of tile rows
     ntiles = q * (q + 1) + ((tiles_m & 1) ? (q + 1) : 0);
   }
-  kern_fwd_kernel<<<ntiles, KF_THREADS, 0, stream>>>(p);
+  switch (kind) {
+    case KERN_RBF: kern_fwd_kernel<KERN_RBF><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+    case KERN_EXP: kern_fwd_kernel<KERN_EXP><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+    case KERN_MATERN32: kern_fwd_kernel<KERN_MATERN32><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+    case KERN_MATERN52: kern_fwd_kernel<KERN_MATERN52><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+    case KERN_LINEAR: kern_fwd_kernel<KERN_LINEAR><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+    default: kern_fwd_kernel<KERN_PERIODIC><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+  }
   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
@@ -253,8 +263,11 @@ struct KbwdParams {
 };
 
 // G2: also accumulate the per-column sums needed for dLoss/dX2 (and for the Linear kernel's variance gradient).
-template <bool GPR, int KB_DC, bool G2>
+// KIND >= 0: the covariance family as a compile-time constant (stationary families); KIND < 0: read p.kind at run time
+// (Linear, Constant, White -- no transcendental in their derivative).
+template <bool GPR, int KB_DC, bool G2, int KIND>
 __global__ void __launch_bounds__(KB_THREADS, 2) kern_bwd_kernel(const KbwdParams p) {
+  const int kind = KIND >= 0 ? KIND : p.kind;
   extern __shared__ double kb_smem[];
   const int D = p.D;
   double* X2s = kb_smem;                       // [D][128]
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(KB_THREADS, 2) kern_bwd_kernel(const KbwdParam
   const int c0 = cb * KB_COLS;
   const int j = c0 + c;
   const bool jvalid = j < p.n2;
-  const bool linear = p.kind == KERN_LINEAR;
+  const bool linear = kind == KERN_LINEAR;
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
 
   for (int d = t; d < D; d += KB_THREADS) ellv[d] = p.ell[p.ell_len == 1 ? 0 : d];
@@ -374,12 +387,12 @@ __global__ void __launch_bounds__(KB_THREADS, 2) kern_bwd_kernel(const KbwdParam
         if (valid) {
           if (linear) {
             h = g;
-          } else if (p.kind >= KERN_CONSTANT) {
+          } else if (kind >= KERN_CONSTANT) {
             // Constant: K = sigma2; White: K = sigma2 [i == j] for K(X), 0 for K(X, X2) (gptorch/kernels.py:83-101)
-            if (dc == 0 && (p.kind == KERN_CONSTANT || (p.symmetric && i == j))) sK += g;
+            if (dc == 0 && (kind == KERN_CONSTANT || (p.symmetric && i == j))) sK += g;
           } else {
             double kbase, fac1;
-            kern_base_fac(p.kind, r2[rr], kbase, fac1);
+            kern_base_fac(kind, r2[rr], kbase, fac1);
             if (dc == 0) sK += g * kbase;
             h = g * fac1 * sig2;
           }
@@ -500,15 +513,27 @@ size_t kern_bwd_workspace_bytes(int n1, int n2, int D) {
   return (ncta * (D + 2) + static_cast<size_t>(strips) * n2 * D) * sizeof(double) + 256;
 }
 
-template <bool GPR, int DC, bool G2>
-static int kbwd_launch_cfg(const KbwdParams& p, int ncb, size_t smem, cudaStream_t stream) {
+template <bool GPR, int DC, bool G2, int KIND>
+static int kbwd_launch_kind(const KbwdParams& p, int ncb, size_t smem, cudaStream_t stream) {
   static int smem_state[GPB_MAX_DEVICES] = {0};
-  if (int rc = ensure_dynamic_smem(kern_bwd_kernel<GPR, DC, G2>, static_cast<int>(smem), smem_state)) return rc;
+  if (int rc = ensure_dynamic_smem(kern_bwd_kernel<GPR, DC, G2, KIND>, static_cast<int>(smem), smem_state)) return rc;
   dim3 grid(ncb, p.strips);
-  kern_bwd_kernel<GPR, DC, G2><<<grid, KB_THREADS, smem, stream>>>(p);
+  kern_bwd_kernel<GPR, DC, G2, KIND><<<grid, KB_THREADS, smem, stream>>>(p);
   count_launch();
   GPB_CUDA_CHECK(cudaGetLastError());
   return GPB_OK;
+}
+
+template <bool GPR, int DC, bool G2>
+static int kbwd_launch_cfg(const KbwdParams& p, int ncb, size_t smem, cudaStream_t stream) {
+  switch (p.kind) {
+    case KERN_RBF: return kbwd_launch_kind<GPR, DC, G2, KERN_RBF>(p, ncb, smem, stream);
+    case KERN_EXP: return kbwd_launch_kind<GPR, DC, G2, KERN_EXP>(p, ncb, smem, stream);
+    case KERN_MATERN32: return kbwd_launch_kind<GPR, DC, G2, KERN_MATERN32>(p, ncb, smem, stream);
+    case KERN_MATERN52: return kbwd_launch_kind<GPR, DC, G2, KERN_MATERN52>(p, ncb, smem, stream);
+    case KERN_PERIODIC: return kbwd_launch_kind<GPR, DC, G2, KERN_PERIODIC>(p, ncb, smem, stream);
+    default: return kbwd_launch_kind<GPR, DC, G2, -1>(p, ncb, smem, stream);
+  }
 }
 
 template <bool GPR>
