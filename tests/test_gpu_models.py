@@ -478,3 +478,71 @@ def test_graphed_bridge_falls_back_for_jitter_and_uncapturable_models(capsys):
     fo, go = ok._loss_and_grad(ok._get_param_array())
     assert np.isfinite(fo) and "_graph_eval" in ok.__dict__
     capsys.readouterr()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# edge cases: empty / ragged / wide inputs
+# ----------------------------------------------------------------------------------------------------------
+def test_empty_and_single_point_inputs():
+    """Zero test points, one training point, zero-row K: shapes follow the reference (torch broadcasting rules)."""
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import GPR
+    rng = np.random.RandomState(0)
+    x, y = rng.rand(30, 3), rng.rand(30, 2)
+    model = GPR(x, y, kernels.Matern52(3, ARD=True), likelihood=likelihoods.Gaussian(variance=0.1))
+    empty = torch.zeros(0, 3, dtype=torch.float64).cuda()
+    with torch.no_grad():
+        mu, var = model._predict(empty, diag=True)
+        assert mu.shape == (0, 2) and var.shape == (0, 2)
+        mu, cov = model._predict(empty, diag=False)
+        assert mu.shape == (0, 2) and cov.shape == (0, 0)
+        assert model.kernel.K(empty).shape == (0, 0)
+        assert model.kernel.K(empty, model.X).shape == (0, 30) and model.kernel.K(model.X, empty).shape == (30, 0)
+        assert model.kernel.Kdiag(empty).shape == (0,)
+    one = GPR(x[:1], y[:1], kernels.Rbf(3), likelihood=likelihoods.Gaussian(variance=0.1))
+    loss = one.loss()
+    loss.backward()
+    # closed form for n = 1: Ky = sigma2 + noise
+    ky = 1.0 + 0.1
+    want = 0.5 * (y[:1] ** 2).sum() / ky + 0.5 * 2 * np.log(ky) + 0.5 * 2 * np.log(2 * np.pi)
+    assert abs(loss.item() - want) < 1e-12 * abs(want)
+    with torch.no_grad():
+        mu, var = one._predict(torch.as_tensor(x[1:4]).cuda(), diag=True)
+    assert mu.shape == (3, 2) and bool((var > 0).all())
+
+
+@pytest.mark.parametrize("d,dy,n", [(1, 1, 257), (33, 7, 300), (160, 2, 140), (9, 5, 129)])
+def test_gpr_wide_inputs_and_many_outputs(d, dy, n):
+    """Input dimensions that are not multiples of the staging chunk (and the largest the backward kernel stages,
+    D = 160), more outputs than one trsv group (4): loss and gradients against the oracle."""
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import GPR
+    g = torch.Generator().manual_seed(d * 100 + dy)
+    X = torch.rand(n, d, generator=g, dtype=torch.float64)
+    Y = torch.randn(n, dy, generator=g, dtype=torch.float64)
+    ell = (1.0 + 0.5 * torch.rand(d, generator=g, dtype=torch.float64)).numpy() * np.sqrt(d)
+    model = GPR(X.numpy(), Y.numpy(), kernels.Matern32(d, ARD=True, length_scales=ell.copy(), variance=1.3),
+                likelihood=likelihoods.Gaussian(variance=0.05))
+    loss = model.loss()
+    loss.backward()
+    h = O.Hyper("Matern32", ell, 1.3, 0.05)
+    ref = -O.gpr_loglik(h, X, Y)
+    ref.sum().backward()
+    assert rel_err(loss.detach().cpu().numpy(), ref.detach().numpy()) <= LML_TOL
+    assert rel_err(model.kernel.length_scales.grad.cpu().numpy(), h.raw_ell.grad.numpy()) <= GRAD_TOL
+    assert rel_err(model.kernel.variance.grad.cpu().numpy(), h.raw_var.grad.numpy()) <= GRAD_TOL
+    assert rel_err(model.likelihood.variance.grad.cpu().numpy(), h.raw_noise.grad.numpy()) <= GRAD_TOL
+
+
+def test_too_wide_inputs_fail_loudly():
+    """D beyond the backward kernel's shared-memory staging (160) is rejected with an error, never silently wrong."""
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200._lib import NativeLibraryError
+    from gptorch_b200.models import GPR
+    rng = np.random.RandomState(0)
+    model = GPR(rng.rand(40, 200), rng.rand(40, 1), kernels.Rbf(200, ARD=True), likelihood=likelihoods.Gaussian(variance=0.1))
+    loss = model.loss()                       # forward has no limit on D
+    assert np.isfinite(loss.item())
+    with pytest.raises(NativeLibraryError):
+        loss.backward()
