@@ -13,6 +13,14 @@ from ..model import Model
 from ..util import TensorType, as_tensor, torch_dtype
 
 
+def _pinned(a):
+    """float64 CPU tensor in page-locked memory (plain pageable memory when no CUDA driver is present)."""
+    t = torch.as_tensor(a, dtype=torch_dtype).detach().cpu().contiguous()
+    if torch.cuda.is_available() and not t.is_pinned():
+        t = t.pin_memory()
+    return t
+
+
 def input_as_tensor(predict_func):
     """Decorator for the public predict_* methods: accept numpy or tensors on any device, run on the model's
     device, hand the result back in the caller's format (gptorch/models/base.py:21-55)."""
@@ -27,10 +35,10 @@ def input_as_tensor(predict_func):
     def predict(obj, input_new, *args, **kwargs):
         from_numpy = isinstance(input_new, np.ndarray)
         if from_numpy:
-            x = torch.as_tensor(input_new, dtype=torch_dtype).to(obj.Y.device)
+            x = torch.as_tensor(input_new, dtype=torch_dtype).to(obj.compute_device)
         else:
             caller_device = input_new.device
-            x = input_new.to(obj.Y.device)
+            x = input_new.to(obj.compute_device)
         out = predict_func(obj, x, *args, **kwargs)
         if from_numpy:
             return convert(out, lambda o: o.detach().cpu().numpy())
@@ -101,16 +109,29 @@ class GPModel(Model):
         store[name] = (key, snap, value)
         return value
 
-    def __init__(self, x, y, kernel, likelihood, mean_function, name="gp"):
+    def __init__(self, x, y, kernel, likelihood, mean_function, name="gp", data_on_host=False):
         super().__init__()
         self.kernel = kernel
         self.likelihood = likelihood if likelihood is not None else GPModel._init_gaussian_likelihood(y)
         self.mean_function = mean_function if mean_function is not None else Zero(y.shape[1])
-        x, y = as_tensor(x), as_tensor(y)
+        self.data_on_host = bool(data_on_host)
+        if self.data_on_host:
+            # data sets larger than HBM: rows stay in page-locked host memory and minibatches are
+            # staged to the device (sparse_gpr.HostBatchStream); only minibatch models can work this way
+            x, y = _pinned(x), _pinned(y)
+        else:
+            x, y = as_tensor(x), as_tensor(y)
         x.requires_grad_(False)
         y.requires_grad_(False)
         self.X, self.Y = x, y   # plain attributes (not buffers), as in the reference
         self.__class__.__name__ = name
+
+    @property
+    def compute_device(self):
+        """Where the numerics run: the data's device, or the parameters' device when the data stay on the host."""
+        if self.data_on_host:
+            return next(self.parameters()).device
+        return self.Y.device
 
     @property
     def num_data(self):
@@ -220,11 +241,13 @@ class GPModel(Model):
     # ---- device moves: the data are attributes, not buffers ---------------------------------------------
     def cuda(self):
         super().cuda()
-        self.X, self.Y = self.X.cuda(), self.Y.cuda()
+        if not self.data_on_host:
+            self.X, self.Y = self.X.cuda(), self.Y.cuda()
 
     def cpu(self):
         super().cpu()
-        self.X, self.Y = self.X.cpu(), self.Y.cpu()
+        if not self.data_on_host:
+            self.X, self.Y = self.X.cpu(), self.Y.cpu()
 
     def _loss(self, *args, **kwargs):
         return -(self.log_likelihood(*args, **kwargs) + self.log_prior())

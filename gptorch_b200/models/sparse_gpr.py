@@ -16,7 +16,7 @@ from ..functions import cholesky, trtrs, mm, mm_nt, mm_tn
 from ..likelihoods import Gaussian
 from ..mean_functions import Zero
 from ..model import Param
-from ..util import as_tensor, kmeans_centers, torch_dtype
+from ..util import KMEANS_HOST_MAX_ROWS, as_tensor, kmeans_centers, kmeans_centers_device, torch_dtype
 from .base import GPModel
 from .gpr import GPR, _native_kind
 
@@ -29,13 +29,16 @@ class _InducingPointsGP(GPModel):
     (gptorch/models/sparse_gpr.py:24-73)."""
 
     def __init__(self, x, y, kernel, num_inducing_points=None, inducing_points=None, mean_function=None,
-                 likelihood=None):
-        super().__init__(x, y, kernel, likelihood, mean_function)
+                 likelihood=None, data_on_host=False):
+        super().__init__(x, y, kernel, likelihood, mean_function, data_on_host=data_on_host)
         if inducing_points is None:
             if num_inducing_points is None:
                 num_inducing_points = np.clip(x.shape[0] // 10, 1, 100)
-            x_host = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
-            inducing_points = kmeans_centers(x_host, num_inducing_points, perturb_if_fail=True)
+            if x.shape[0] > KMEANS_HOST_MAX_ROWS and torch.cuda.is_available():
+                inducing_points = kmeans_centers_device(x, num_inducing_points)
+            else:
+                x_host = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
+                inducing_points = kmeans_centers(x_host, num_inducing_points, perturb_if_fail=True)
         self.Z = Param(as_tensor(inducing_points))
         self._group = None          # torch.distributed process group when the rows of X are sharded
         self._num_data_global = None
@@ -49,7 +52,7 @@ class _InducingPointsGP(GPModel):
         every rank after torch.distributed.init_process_group."""
         import torch.distributed as dist
         self._group = group if group is not None else dist.group.WORLD
-        n = torch.tensor([float(self.Y.shape[0])], dtype=torch_dtype, device=self.Y.device)
+        n = torch.tensor([float(self.Y.shape[0])], dtype=torch_dtype, device=self.compute_device)
         dist.all_reduce(n, group=self._group)
         self._num_data_global = int(n.item())
         return self
@@ -127,6 +130,73 @@ class VFE(_InducingPointsGP):
         return mean, var
 
 
+def draw_minibatch_indices(n, batch_size):
+    """Indices of a minibatch drawn without replacement from n rows (numpy int64)."""
+    if n <= MINIBATCH_PERMUTE_MAX:
+        return np.random.permutation(n)[:batch_size]        # the reference's draw, same RNG stream
+    # O(batch) draw without replacement: a full permutation of 1e8 indices per step is 0.8 GB of host work
+    return np.random.default_rng(np.random.randint(1 << 31)).choice(n, size=batch_size, replace=False)
+
+
+class HostBatchStream:
+    """Minibatches of a data set that stays in page-locked HOST memory (N = 1e8 rows of D = 32 are
+    25.6 GB; a data set beyond HBM cannot be indexed on the device like gptorch/models/sparse_gpr.py:209-211 does).
+
+    next() hands out the batch whose rows were gathered into a pinned staging buffer and copied to the device on a
+    side stream WHILE the previous step was computing, then starts gathering the following batch on a worker thread
+    (torch.index_select releases the GIL).  Two staging buffers per tensor; a CUDA event per buffer keeps the worker
+    from overwriting a buffer whose host-to-device copy is still in flight.  Indices come from the same host RNG
+    stream as the resident path, one draw per batch, in order.
+    """
+
+    def __init__(self, X, Y, batch_size, device):
+        import threading
+        self.X, self.Y, self.b, self.dev = X, Y, int(batch_size), device
+        pin = torch.cuda.is_available()
+        self.stage = [(torch.empty((self.b, X.shape[1]), dtype=X.dtype, pin_memory=pin),
+                       torch.empty((self.b, Y.shape[1]), dtype=Y.dtype, pin_memory=pin)) for _ in range(2)]
+        self.copied = [None, None]            # event: the H2D copy out of staging buffer k has completed
+        self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self._threading = threading
+        self.k = 0
+        self.pending = None
+        self._start()
+
+    def _gather(self, k, idx):
+        if self.copied[k] is not None:
+            self.copied[k].synchronize()
+        sx, sy = self.stage[k]
+        torch.index_select(self.X, 0, idx, out=sx)
+        torch.index_select(self.Y, 0, idx, out=sy)
+
+    def _start(self):
+        idx = torch.from_numpy(np.ascontiguousarray(draw_minibatch_indices(self.Y.shape[0], self.b), dtype=np.int64))
+        th = self._threading.Thread(target=self._gather, args=(self.k, idx), daemon=True)
+        th.start()
+        self.pending = (self.k, th)
+        self.k ^= 1
+
+    def next(self):
+        k, th = self.pending
+        th.join()
+        sx, sy = self.stage[k]
+        if self.stream is None:
+            x, y = sx.clone(), sy.clone()
+        else:
+            cur = torch.cuda.current_stream(self.dev)
+            with torch.cuda.stream(self.stream):
+                x = sx.to(self.dev, non_blocking=True)
+                y = sy.to(self.dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self.copied[k] = ev
+            cur.wait_stream(self.stream)
+            x.record_stream(cur)
+            y.record_stream(cur)
+        self._start()
+        return x, y
+
+
 def minibatch(loss_func):
     """Draw a random subset of the data when none is given (gptorch/models/sparse_gpr.py:198-216)."""
 
@@ -134,14 +204,16 @@ def minibatch(loss_func):
         if x is not None:
             assert y is not None
         elif obj.batch_size is not None:
-            n = obj.Y.shape[0]
-            if n <= MINIBATCH_PERMUTE_MAX:
-                i = np.random.permutation(n)[: obj.batch_size]        # the reference's draw, same RNG stream
+            if obj.data_on_host:
+                stream = obj.__dict__.get("_host_stream")
+                if stream is None or stream.b != obj.batch_size:
+                    stream = obj.__dict__["_host_stream"] = HostBatchStream(obj.X, obj.Y, obj.batch_size, obj.compute_device)
+                x, y = stream.next()
             else:
-                # O(batch) draw without replacement: a full permutation of 1e8 indices per step is 0.8 GB of host work
-                i = np.random.default_rng(np.random.randint(1 << 31)).choice(n, size=obj.batch_size, replace=False)
-            i = torch.as_tensor(i, device=obj.X.device)
-            x, y = obj.X[i, :], obj.Y[i, :]
+                i = torch.as_tensor(draw_minibatch_indices(obj.Y.shape[0], obj.batch_size), device=obj.X.device)
+                x, y = obj.X[i, :], obj.Y[i, :]
+        elif obj.data_on_host:
+            raise ValueError("a model whose data stay on the host needs batch_size (or explicit x, y)")
         else:
             x, y = obj.X, obj.Y
         return loss_func(obj, x, y)
@@ -153,13 +225,13 @@ class SVGP(_InducingPointsGP):
     """Sparse variational GP with an explicit Gaussian q(u) = N(induced_output_mean + m(Z), L_S L_S^T)."""
 
     def __init__(self, y, x, kernel, num_inducing_points=None, inducing_points=None, mean_function=None,
-                 likelihood=None, batch_size=None):
+                 likelihood=None, batch_size=None, data_on_host=False):
         # NB the first two positional arguments are (inputs, outputs) despite their names -- the reference
         # swaps the names but passes them through positionally (gptorch/models/sparse_gpr.py:230-253).
         if likelihood is None:
             likelihood = Gaussian()
         super().__init__(y, x, kernel, num_inducing_points=num_inducing_points, inducing_points=inducing_points,
-                         mean_function=mean_function, likelihood=likelihood)
+                         mean_function=mean_function, likelihood=likelihood, data_on_host=data_on_host)
         self.batch_size = batch_size
         self.induced_output_mean, self.induced_output_chol_cov = self._init_posterior()
 
@@ -195,7 +267,7 @@ class SVGP(_InducingPointsGP):
         """Initial q(u) from an exact GP on at most 100 random points (gptorch/models/sparse_gpr.py:310-335)."""
         i = np.random.permutation(self.Y.shape[0])[0: min(self.Y.shape[0], 100)]
         idx = torch.as_tensor(i, device=self.X.device)
-        x, y = self.X[idx], self.Y[idx]
+        x, y = self.X[idx].to(self.compute_device), self.Y[idx].to(self.compute_device)
         likelihood = self.likelihood if isinstance(self.likelihood, Gaussian) else Gaussian(variance=0.01 * float(y.var()))
         model = GPR(x, y, self.kernel, mean_function=self.mean_function, likelihood=likelihood)
         with torch.no_grad():

@@ -546,3 +546,77 @@ def test_too_wide_inputs_fail_loudly():
     assert np.isfinite(loss.item())
     with pytest.raises(NativeLibraryError):
         loss.backward()
+
+
+def test_svgp_data_on_host_stream_matches_resident_minibatches():
+    """with data_on_host=True the rows stay in pinned host memory and minibatches are gathered and
+    copied one step ahead (HostBatchStream); the sequence of minibatches -- hence every loss and gradient -- is the
+    same as with device-resident data and the same host RNG stream."""
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import SVGP
+    X, Y, g = O.synth_regression(5000, 4)
+    Z = O.synth_inducing(X, 24, g).numpy()
+
+    def build(on_host):
+        np.random.seed(0)
+        return SVGP(X.numpy(), Y.numpy(), kernels.Matern52(4, ARD=True), inducing_points=Z,
+                    likelihood=likelihoods.Gaussian(variance=0.05), batch_size=700, data_on_host=on_host)
+
+    def run(model):
+        np.random.seed(123)
+        out = []
+        for _ in range(4):
+            for p in model.parameters():
+                p.grad = None
+            loss = model.loss()
+            loss.backward()
+            out.append((loss.item(), model.Z.grad.clone(), model.kernel.length_scales.grad.clone()))
+        return out
+
+    resident, hosted = build(False), build(True)
+    assert resident.X.is_cuda and not hosted.X.is_cuda and hosted.X.is_pinned()
+    assert hosted.compute_device.type == "cuda" and hosted.num_data == 5000 and not hosted._graphable()
+    a, b = run(resident), run(hosted)
+    for (la, gza, gla), (lb, gzb, glb) in zip(a, b):
+        assert la == lb and torch.equal(gza, gzb) and torch.equal(gla, glb)
+    assert len({l for l, _, _ in a}) == 4                    # four different minibatches
+    with torch.no_grad():                                    # prediction never touches the host data
+        mu, var = hosted.predict_f(X[:9].numpy())
+    assert mu.shape == (9, 1) and np.all(var > 0)
+    hosted.batch_size = None
+    with pytest.raises(ValueError):
+        hosted.loss()
+
+
+def test_device_kmeans_for_large_data():
+    """util.kmeans_centers_device (used for the default inducing inputs above 200k rows): centres land on the clusters,
+    are reproducible under the numpy seed, and a VFE built without inducing_points uses it."""
+    from gptorch_b200 import kernels, util
+    from gptorch_b200.models import VFE
+    rng = np.random.RandomState(1)
+    true = rng.rand(6, 3) * 10.0
+    lab = rng.randint(0, 6, size=60000)
+    x = true[lab] + 0.05 * rng.randn(60000, 3)
+    np.random.seed(5)
+    c1 = util.kmeans_centers_device(x, 6, iters=25, chunk=7000)       # ragged chunks
+    np.random.seed(5)
+    c2 = util.kmeans_centers_device(x, 6, iters=25, chunk=7000)
+    assert c1.shape == (6, 3) and np.array_equal(c1, c2)
+    # Lloyd fixed point: every centre is the mean of the rows nearest to it
+    d2 = ((x[:, None, :] - c1[None, :, :]) ** 2).sum(-1)
+    a = d2.argmin(1)
+    for j in range(6):
+        if (a == j).any():
+            assert np.allclose(c1[j], x[a == j].mean(0), atol=1e-9)
+    # inertia no worse than assigning to the true centres by more than the noise level
+    assert d2.min(1).mean() < 4 * 3 * 0.05 ** 2 + ((x - true[lab]) ** 2).sum(1).mean() * 50
+    old = util.KMEANS_HOST_MAX_ROWS
+    import gptorch_b200.models.sparse_gpr as sg
+    sg.KMEANS_HOST_MAX_ROWS = 1000
+    try:
+        np.random.seed(2)
+        m = VFE(x[:5000], rng.rand(5000, 1), kernels.Rbf(3), num_inducing_points=6)
+    finally:
+        sg.KMEANS_HOST_MAX_ROWS = old
+    assert m.Z.shape == (6, 3) and m.Z.is_cuda and np.isfinite(m.loss().item())
