@@ -1,34 +1,38 @@
-"""Parameters with a constraint transform and an optional prior (reference: gptorch/param.py:13-50)."""
+"""Constrained parameters (reference API: gptorch/param.py:13-50).
+
+A `Param` is a torch Parameter that holds the UNCONSTRAINED number the optimiser moves and remembers the bijection
+to the constrained value the model uses: `Param(v, transform=t)` stores t^-1(v) and `.transform()` evaluates t(raw).
+Positive quantities (variances, length scales) use exp, so `.grad` is a gradient with respect to the logarithm; a
+`prior` (any torch.distributions object) is evaluated on the constrained value by Model.log_prior.
+"""
 import torch
 from torch.distributions.transforms import ComposeTransform
 
+_IDENTITY = ComposeTransform([])
 
-def _as_transform(t):
-    return ComposeTransform([]) if t is None else t
+
+def _bijection(transform):
+    """The transform to use: the identity when none was given."""
+    return transform if transform is not None else _IDENTITY
 
 
 class Param(torch.nn.Parameter):
-    """torch Parameter that stores the UNCONSTRAINED value.
-
-    ``Param(v, transform=t)`` stores ``t.inv(v)``; ``.transform()`` returns the constrained value ``t(raw)``.
-    Optimisers and ``.grad`` therefore see the raw value (log-space for positive quantities).
-    """
-
     def __new__(cls, data=None, requires_grad=True, transform=None, prior=None):
-        raw = _as_transform(transform).inv(data)
-        return super().__new__(cls, raw, requires_grad=requires_grad)
+        unconstrained = _bijection(transform).inv(data)
+        return torch.nn.Parameter.__new__(cls, unconstrained, requires_grad)
 
     def __init__(self, data, requires_grad=True, transform=None, prior=None):
-        super().__init__()
-        self._transform = _as_transform(transform)
+        torch.nn.Parameter.__init__(self)
         self.prior = prior
+        self._transform = _bijection(transform)
 
     def transform(self):
+        """Constrained value t(raw), differentiable with respect to the raw storage."""
         return self._transform(self)
-
-    def __repr__(self):
-        return "Parameter containing:" + self.data.__repr__()
 
     @staticmethod
     def _validate_transform(t):
-        return _as_transform(t)
+        return _bijection(t)
+
+    def __repr__(self):
+        return "Parameter containing:" + repr(self.data)
