@@ -343,7 +343,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:     # reported on rank 0 of the single-GPU run only
         line["cpu_baseline"] = cpu_baseline(n, args.cpu_sample_n)
     print(json.dumps(line), flush=True)
 
