@@ -11,7 +11,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--num-points", dest="n", type=int, default=131072)
     ap.add_argument("--dim", dest="d", type=int, default=8)
-    ap.add_argument("--panel", type=int, default=2048)
+    ap.add_argument("--panel", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--check", action="store_true", help="compare with the single-GPU GPR loss (N must fit one GPU)")
