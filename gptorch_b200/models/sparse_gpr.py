@@ -206,7 +206,7 @@ def minibatch(loss_func):
         elif obj.batch_size is not None:
             if obj.data_on_host:
                 stream = obj.__dict__.get("_host_stream")
-                if stream is None or stream.b != obj.batch_size:
+                if stream is None or stream.b != obj.batch_size or stream.X is not obj.X or stream.Y is not obj.Y:
                     stream = obj.__dict__["_host_stream"] = HostBatchStream(obj.X, obj.Y, obj.batch_size, obj.compute_device)
                 x, y = stream.next()
             else:
