@@ -620,3 +620,28 @@ def test_device_kmeans_for_large_data():
     finally:
         sg.KMEANS_HOST_MAX_ROWS = old
     assert m.Z.shape == (6, 3) and m.Z.is_cuda and np.isfinite(m.loss().item())
+
+
+def test_graphed_bridge_rebuilds_when_storage_is_replaced(capsys):
+    """The captured graph reads parameters and data at fixed addresses: replacing a Param's storage or the data
+    tensors must rebuild it (never replay against stale memory)."""
+    graphed = _bridge_model("GPR")
+    theta = graphed._get_param_array()
+    f0, g0 = graphed._loss_and_grad(theta)
+    first = graphed.__dict__["_graph_eval"]
+    # same storage: the same graph object is replayed
+    graphed._loss_and_grad(theta + 0.1)
+    assert graphed.__dict__["_graph_eval"] is first
+    # a Param gets new storage (what p.data = ... does in user code)
+    graphed.kernel.variance.data = graphed.kernel.variance.data.clone()
+    f1, g1 = graphed._loss_and_grad(theta)
+    second = graphed.__dict__["_graph_eval"]
+    assert second is not first and f1 == f0 and np.array_equal(g1, g0)
+    # new targets: the loss must change accordingly (no replay against the old Y)
+    graphed.Y = graphed.Y * 2.0
+    f2, _ = graphed._loss_and_grad(theta)
+    fresh = _bridge_model("GPR")
+    fresh.Y = fresh.Y * 2.0
+    f3, _ = fresh._loss_and_grad(theta)
+    assert graphed.__dict__["_graph_eval"] is not second and f2 == f3 and f2 != f0
+    capsys.readouterr()
