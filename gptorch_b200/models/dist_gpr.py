@@ -427,14 +427,82 @@ class DistributedGPR(GPR):
         self._panel = panel
         self._side = None
 
+    def _kind(self):
+        kind = _native_kind(self.kernel)
+        if kind is None or not isinstance(self.likelihood, Gaussian):
+            raise NotImplementedError("DistributedGPR needs a stationary kernel and the Gaussian likelihood")
+        return kind
+
+    def _posterior_state(self, x):
+        """(slabs holding Ky^-1 as a lower block triangle, a = Ky^-1 (Y - m(x))) -- what every prediction needs.
+        Built by the factorisation and stages 1-2 of the gradient, cached per parameter / data state (GPModel._memo)."""
+        def compute():
+            xc = nv._c(x.to(torch.float64))
+            _, st = _factorise(self._ops, self._kind(), xc, self.Y - self.mean_function(xc),
+                               self.kernel.length_scales.transform(), self.kernel.variance.transform(),
+                               self.likelihood.variance.transform(), self._panel, self._group, self._side)
+            a = _invert_factor(st)
+            _inverse_from_t(st)
+            return st, a
+
+        return self._memo("dist_posterior", x, compute)
+
+    @torch.no_grad()
+    def _predict(self, x_new, diag=True, x=None, block=1024):
+        """p(f* | y) (gptorch/models/gpr.py:88-117) with the training covariance spread over the ranks: the mean is
+        K(x*, X) a with the replicated a = Ky^-1 r; the quadratic form k*^T Ky^-1 k* is summed slab by slab from the
+        distributed inverse (diagonal blocks once, blocks below the diagonal twice) and all-reduced.  Test points are
+        processed in blocks so that K(X, x*) never exceeds N x `block`.  Collective; not differentiable."""
+        x = x if x is not None else self.X
+        if self._side is None and x.is_cuda:
+            self._side = torch.cuda.Stream(priority=-1)
+        st, a = self._posterior_state(x)
+        ops, kind = self._ops, st.kind
+        ell, s2 = self.kernel.length_scales.transform(), self.kernel.variance.transform()
+        xs_all = nv._c(x_new.to(torch.float64))
+        xc = nv._c(x.to(torch.float64))
+        ns, dy, w = xs_all.shape[0], st.dy, st.w
+        dev = xc.device
+        mean = torch.zeros((ns, dy), dtype=torch.float64, device=dev)
+        quad = torch.zeros(ns if diag else (ns, ns), dtype=torch.float64, device=dev)
+        if not diag:
+            block = max(ns, 1)              # the full covariance needs every pair of test points at once
+        for b0 in range(0, ns, block):
+            xs = xs_all[b0: b0 + block]
+            nb = xs.shape[0]
+            for j in st.mine:
+                c, wj = st.cols[j]
+                s0 = st.slot[j] * w
+                Ks = ops.empty(st.n - c, nb, dev)[:, :nb]
+                ops.kern_fill(kind, xc[c:], xs, ell, s2, Ks, Ks.stride(0))          # K(X[c:], x*)
+                Kj = Ks[:wj].clone()
+                # this rank's share of the mean: block column j of K(x*, X) times a_j
+                mean[b0: b0 + nb] += ops.gemm(ops.GEMM_TN, Kj, a[c:c + wj])
+                Ks[:wj].mul_(0.5)
+                Z = ops.gemm(ops.GEMM_TN, st.A[c:, s0:s0 + wj], Ks)                  # (wj x nb)
+                if diag:
+                    quad[b0: b0 + nb] += 2.0 * (Z * Kj).sum(0)
+                else:
+                    S = ops.gemm(ops.GEMM_TN, Z, Kj)
+                    quad += S + S.t()
+        flat = torch.cat([mean.reshape(-1), quad.reshape(-1)])
+        dist.all_reduce(flat, group=self._group)
+        mean = flat[: ns * dy].reshape(ns, dy) + self.mean_function(xs_all)
+        quad = flat[ns * dy:].reshape(quad.shape)
+        if diag:
+            var = (s2.reshape(()) - quad)[:, None].expand(ns, dy)
+        else:
+            Kss = ops.empty(ns, ns, dev)[:, :ns]
+            ops.kern_fill(kind, xs_all, None, ell, s2, Kss, Kss.stride(0))
+            var = Kss - quad
+        return mean, var
+
     def log_likelihood(self, x=None, y=None):
         x = x if x is not None else self.X
         y = y if y is not None else self.Y
         if x.shape[0] != y.shape[0]:
             raise ValueError("X and Y must have same # data.")
-        kind = _native_kind(self.kernel)
-        if kind is None or not isinstance(self.likelihood, Gaussian):
-            raise NotImplementedError("DistributedGPR needs a stationary kernel and the Gaussian likelihood")
+        kind = self._kind()
         if x.is_cuda and self._side is None:
             self._side = torch.cuda.Stream(priority=-1)
         x = nv._c(x.to(torch.float64))

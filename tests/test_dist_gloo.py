@@ -128,7 +128,7 @@ class _TorchOps:
 
     def kern_fill(self, kind, Xr, Xc, ell, s2, out, ld):
         from oracle import gp_oracle as O
-        out[:, : Xc.shape[0]] = O.cov(self.NAMES[kind], Xr, Xc, ell, s2)
+        out[:, : (Xr if Xc is None else Xc).shape[0]] = O.cov(self.NAMES[kind], Xr, Xc, ell, s2)
 
     def add_diag(self, blk, ld, value):
         blk.diagonal().add_(value.reshape(()))
@@ -190,7 +190,19 @@ def _dist_gpr_loss_and_grad(rank, world, n=203, panel=32, kind="Matern52"):
     got = {"variance": model.kernel.variance.grad, "length_scales": model.kernel.length_scales.grad,
            "noise": model.likelihood.variance.grad}
     rel = lambda a, b: float((a.reshape(-1) - b.reshape(-1)).abs().max() / b.abs().max())  # noqa: E731
-    return (abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()), {k: rel(got[k], ref[k]) for k in ref})
+    errs = {k: rel(got[k], ref[k]) for k in ref}
+    # distributed prediction (mean, variance, full covariance) against the oracle's single-process posterior
+    Xs = torch.rand(11, d, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    h = O.Hyper(kind, ell, var, noise)
+    with torch.no_grad():
+        mu_ref, var_ref = O.gpr_predict(h, X, Y, Xs, diag=True)
+        _, cov_ref = O.gpr_predict(h, X, Y, Xs, diag=False)
+    mu, v = model._predict(Xs, diag=True, block=4)            # several blocks of test points, ragged
+    mu2, cov = model._predict(Xs, diag=False)
+    errs["pred_mean"] = max(rel(mu, mu_ref), rel(mu2, mu_ref))
+    errs["pred_var"] = float((v - var_ref).abs().max() / cov_ref.abs().max())
+    errs["pred_cov"] = float((cov - cov_ref).abs().max() / cov_ref.abs().max())
+    return (abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()), errs)
 
 
 @pytest.mark.parametrize("world,n,panel", [(2, 203, 32), (3, 130, 16), (2, 64, 64)])

@@ -373,6 +373,18 @@ def _dist_gpr_worker(rank, world, port, n, panel, ret):
         assert compared == 3        # kernel variance, length scales, noise
         with torch.no_grad():                       # loss-only evaluation frees the slabs without a backward pass
             again = dm.loss().item()
+            # distributed prediction against the single-GPU posterior (several ragged blocks of test points)
+            Xs = torch.rand(37, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(3)).cuda()
+            mu_ref, var_ref = sm._predict(Xs, diag=True)
+            _, cov_ref = sm._predict(Xs, diag=False)
+            mu, var = dm._predict(Xs, diag=True, block=16)
+            mu2, cov = dm._predict(Xs, diag=False)
+            scale = float(cov_ref.abs().max())
+            pred = [float((mu - mu_ref).abs().max() / mu_ref.abs().max()), float((mu2 - mu_ref).abs().max() / mu_ref.abs().max()),
+                    float((var - var_ref).abs().max()) / scale, float((cov - cov_ref).abs().max()) / scale]
+            assert max(pred) <= PRED_TOL, pred
+            out = dm.predict_y(Xs.cpu().numpy())        # public wrapper: numpy in, numpy out
+            assert out[0].shape == (37, 1) and np.all(out[1] > 0)
         errs.append(abs(again - loss.item()) / abs(loss.item()))
         ret[rank] = errs
     finally:
