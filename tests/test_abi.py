@@ -51,3 +51,20 @@ def test_header_cites_reference_call_sites():
     for cite in ("gptorch/kernels.py", "gptorch/functions.py:46-47", "gptorch/functions.py:71-76",
                  "gptorch/functions.py:61-68", "gptorch/models/gpr.py", "gptorch/util.py:73-88"):
         assert cite in text
+
+
+def test_plain_c_client_compiles_links_and_validates_arguments(tmp_path):
+    """include/gpb200.h is a C header (C99, -pedantic) and the library is usable from plain C: a C program resolves
+    every entry point with dlsym and gets the documented status codes from argument validation -- no GPU needed."""
+    import subprocess
+    from gptorch_b200 import _lib
+    src = os.path.join(ROOT, "tests", "abi", "abi_check.c")
+    exe = str(tmp_path / "abi_check")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    src, "-o", exe, "-ldl"], check=True)
+    out = subprocess.run([exe, _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    fns = _header_functions()
+    assert "abi_check: %d symbols ok" % len(fns) in out, out
+    # the C program's symbol list is the header's
+    listed = set(re.findall(r'"(gpb_\w+)"', open(src).read()))
+    assert listed == set(fns)
