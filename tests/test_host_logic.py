@@ -150,3 +150,25 @@ def test_importing_package_keeps_torch_default_dtype():
     assert util.as_tensor(np.zeros((2, 2), dtype=np.float32)).dtype == torch.float64
     with pytest.raises(TypeError):
         util.as_tensor("nope")
+
+
+def test_host_batch_stream_sequence_matches_the_rng_stream():
+    """HostBatchStream (minibatches of host-resident data) hands out, in order, exactly the rows the
+    host RNG draws -- one draw per batch -- while gathering the next batch on a worker thread (CPU device: no copies)."""
+    import numpy as np
+    from gptorch_b200.models.sparse_gpr import HostBatchStream, draw_minibatch_indices
+    rng = np.random.RandomState(0)
+    X = torch.as_tensor(rng.rand(500, 3))
+    Y = torch.as_tensor(rng.rand(500, 2))
+    np.random.seed(11)
+    expect = [draw_minibatch_indices(500, 64) for _ in range(5)]
+    np.random.seed(11)
+    stream = HostBatchStream(X, Y, 64, torch.device("cpu"))
+    for idx in expect[:4]:                      # the stream is always one draw ahead
+        x, y = stream.next()
+        assert torch.equal(x, X[idx]) and torch.equal(y, Y[idx])
+    assert len({tuple(i) for i in map(tuple, expect)}) == 5
+    # large-N draw: O(batch), without replacement
+    from gptorch_b200.models import sparse_gpr as sg
+    big = draw_minibatch_indices(sg.MINIBATCH_PERMUTE_MAX + 5, 1000)
+    assert len(set(big.tolist())) == 1000 and big.max() < sg.MINIBATCH_PERMUTE_MAX + 5
