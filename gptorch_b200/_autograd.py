@@ -253,6 +253,58 @@ class TrsmRightFn(Function):
         return gX, gL, None
 
 
+class TrsmLeftTFn(Function):
+    """X = L^-T B for many right-hand sides (functions.trtrs with an upper-triangular matrix, lower=False,
+    gptorch/functions.py:71-76), as one product with the dense upper-triangular T = L^-T; differentiable in B and L."""
+
+    @staticmethod
+    def forward(ctx, B, L, dinv):
+        T = _tinv(nv._gemm_operand(L.detach()), dinv)
+        X = nv.gemm(nv.GEMM_NN, T, nv._c(B), flags=nv.GF_KLO_M)      # T[m][k] = 0 for k < m
+        ctx.save_for_backward(T, X)
+        return X
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        T, X = ctx.saved_tensors
+        gB = nv.gemm(nv.GEMM_TN, T, nv._c(G))                         # L^-1 G = T^T G
+        gL = None
+        if ctx.needs_input_grad[1]:                                   # X = L^-T B:  dL = -tril(X gB^T)
+            gL = nv.gemm(nv.GEMM_NT, X, gB, alpha=-1.0, lower_only=True)
+            gL.tril_()
+        return gB if ctx.needs_input_grad[0] else None, gL, None
+
+
+class CholeskyInverseFn(Function):
+    """(L L^T)^-1 from a lower Cholesky factor (functions.cholesky_inverse, gptorch/functions.py:50-54): blocked
+    trtri + lauum in place, assembled to a full symmetric matrix.  backward: with S = G + G^T,
+    dL = -tril(Kinv S L^-T)."""
+
+    @staticmethod
+    def forward(ctx, L):
+        buf, ld = nv.sym_buffer_from(L.detach())
+        dinv = nv.tri_diag_inverse(buf)
+        ctx.save_for_backward(L.detach(), dinv)
+        kd = nv.potri_(buf, ld, dinv)
+        Kinv = nv.potri_assemble(buf, ld, kd)
+        ctx.kinv = Kinv
+        return Kinv
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        L, dinv = ctx.saved_tensors
+        Kinv, ctx.kinv = ctx.kinv, None
+        G = nv._c(G)
+        S = nv._c(G + G.t())
+        T = _tinv(nv._gemm_operand(L), dinv)
+        M1 = nv.gemm(nv.GEMM_NN, Kinv, S)
+        gL = nv.gemm(nv.GEMM_NN, M1, T, alpha=-1.0, flags=nv.GF_KHI_N)   # T[k][n] = 0 for k > n
+        gL.tril_()
+        return gL
+
+
 class LogDetFn(Function):
     """sum(log(diag(L)))  (functions.lt_log_determinant, gptorch/functions.py:61-68)."""
 

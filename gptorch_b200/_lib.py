@@ -111,8 +111,16 @@ def stream_ptr():
     return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
+_keep = []   # tensors whose pointers were taken for the call being assembled (see ptr / call)
+
+
 def ptr(t):
-    """Device pointer of a CUDA fp64 tensor (or NULL for None)."""
+    """Device pointer of a CUDA fp64 tensor (or NULL for None).
+
+    The tensor is kept alive until the entry point it is passed to has been issued: wrappers hand in temporaries such
+    as ``ptr(_c(sigma2).reshape(-1))``, and a temporary freed before the launch could be handed out again by the
+    caching allocator to the next conversion.  The tensor must live on the CURRENT device -- launches go to the current
+    device's current stream."""
     if t is None:
         return None
     if not t.is_cuda:
@@ -120,13 +128,20 @@ def ptr(t):
                                  % t.device.type)
     if t.dtype != torch.float64 and t.dtype != torch.int32:
         raise NativeLibraryError("expected float64, got %s" % t.dtype)
+    if t.device.index != torch.cuda.current_device():
+        raise NativeLibraryError("tensor on %s but the current CUDA device is cuda:%d -- run the call under "
+                                 "torch.cuda.device(tensor.device)" % (t.device, torch.cuda.current_device()))
+    _keep.append(t)
     return ctypes.c_void_p(t.data_ptr())
 
 
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    try:
+        rc = getattr(lib, name)(*args)
+    finally:
+        _keep.clear()
     _check(rc, name)
 
 

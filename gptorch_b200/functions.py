@@ -45,13 +45,11 @@ jitchol = cholesky  # name used by BASELINE.json's north_star
 
 
 def cholesky_inverse(x, upper=False):
-    """(L L^T)^-1 from a Cholesky factor (gptorch/functions.py:50-54); forward-only native path."""
+    """(L L^T)^-1 from a Cholesky factor (gptorch/functions.py:50-54); differentiable in the factor."""
     L = x.t() if upper else x
-    n = L.shape[0]
-    buf, ld = nv.sym_buffer_from(L.detach())
-    dinv = nv.tri_diag_inverse(buf)
-    kd = nv.potri_(buf, ld, dinv)
-    return nv.potri_assemble(buf, ld, kd)
+    if L.dim() != 2 or L.shape[0] != L.shape[1]:
+        raise ValueError("cholesky_inverse expects a square matrix")
+    return ag.CholeskyInverseFn.apply(L)
 
 
 def inverse(x):
@@ -79,8 +77,7 @@ def trtrs(b, a, lower=True):
         return ag.TrsvFn.apply(b, L, dinv, trans)
     if not trans:
         return ag.TrsmRightFn.apply(b.t(), L, dinv).t()      # (b^T L^-T)^T = L^-1 b
-    T = ag._tinv(L.detach(), dinv)                           # L^-T, dense upper
-    return ag.GemmFn.apply(nv.GEMM_NN, T, b)
+    return ag.TrsmLeftTFn.apply(b, L, dinv)                  # L^-T b, differentiable in b and a
 
 
 def mm_nt(a, b):

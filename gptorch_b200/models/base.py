@@ -83,30 +83,42 @@ class GPModel(Model):
     """Base class of the GP models."""
 
     # ---- prediction-time cache of factorisations (SURVEY 8f row 1) ---------------------------------------
-    def _param_snapshot(self):
-        """Values of every parameter as one small device vector (compared bit for bit with the cached one: robust
-        against in-place edits of `.data`, which do not bump version counters)."""
-        return torch.cat([p.detach().reshape(-1).to(torch.float64) for p in self.parameters()])
+    def _param_snapshot(self, x):
+        """Values of every parameter plus checksums of the device-resident data as one small device vector, compared
+        bit for bit with the cached one: robust against in-place edits through `.data` (which do not bump version
+        counters) and against a new tensor allocated at a recycled address."""
+        parts = [p.detach().reshape(-1).to(torch.float64) for p in self.parameters()]
+        for t in (x, self.Y):
+            if t.is_cuda and t.numel():
+                parts.append(torch.stack([t.sum(dtype=torch.float64), torch.linalg.vector_norm(t).to(torch.float64)]))
+        return torch.cat(parts)
+
+    @staticmethod
+    def _tensor_key(t):
+        return (id(t), t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.storage_offset(), str(t.device))
 
     def _memo(self, name, x, compute):
         """compute() -- the parameter- and data-dependent part of a prediction (Cholesky factors, solved
-        right-hand sides) -- evaluated once per (parameters, training inputs, targets) state.
+        right-hand sides) -- evaluated once per (parameters, training inputs, targets, model structure) state.
 
         The reference recomputes these on every _predict call (gptorch/models/gpr.py:104,
         gptorch/models/sparse_gpr.py:169-183, :358).  Only active under torch.no_grad(): with autograd enabled the
-        result is recomputed so that predictions stay differentiable exactly as in the reference.  The key is the
-        identity of the data (storage + in-place version counters) plus a bit-exact parameter snapshot.
+        result is recomputed so that predictions stay differentiable exactly as in the reference.  A hit needs: the
+        very same x / Y tensor objects (the entry keeps them alive, so their ids cannot be recycled) with unchanged
+        version counters, layout and device; the same sub-module objects (kernel, likelihood, mean function and their
+        children); and a bit-exact match of the parameter values and of the data checksums.
         """
         if torch.is_grad_enabled():
             return compute()
-        key = ((x.data_ptr(), x._version, tuple(x.shape)), (self.Y.data_ptr(), self.Y._version, tuple(self.Y.shape)))
-        snap = self._param_snapshot()
+        key = (self._tensor_key(x), self._tensor_key(self.Y), tuple((id(m), type(m)) for m in self.modules()))
+        snap = self._param_snapshot(x)
         store = self.__dict__.setdefault("_memo_store", {})
         hit = store.get(name)
-        if hit is not None and hit[0] == key and hit[1].shape == snap.shape and torch.equal(hit[1], snap):
+        if (hit is not None and hit[0] == key and hit[3] is x and hit[4] is self.Y and hit[1].shape == snap.shape
+                and torch.equal(hit[1], snap)):
             return hit[2]
         value = compute()
-        store[name] = (key, snap, value)
+        store[name] = (key, snap, value, x, self.Y)
         return value
 
     def __init__(self, x, y, kernel, likelihood, mean_function, name="gp", data_on_host=False):

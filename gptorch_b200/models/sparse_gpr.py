@@ -49,9 +49,18 @@ class _InducingPointsGP(GPModel):
 
     def distribute(self, group=None):
         """Declare that self.X / self.Y hold this rank's shard of the rows.  Must be called on
-        every rank after torch.distributed.init_process_group."""
+        every rank after torch.distributed.init_process_group and before the first loss().
+
+        Every parameter (kernel, likelihood, Z, q(u)) is REPLICATED: the summed statistics / gradients are only the
+        global bound if all ranks evaluate them at the same values.  The initialisers depend on the local shard and
+        the local RNG (k-means for Z, SVGP._init_posterior), so the values of the group's first rank are broadcast
+        here; afterwards identical optimiser steps on the all-reduced gradients keep the replicas equal."""
         import torch.distributed as dist
         self._group = group if group is not None else dist.group.WORLD
+        src = dist.get_global_rank(self._group, 0)
+        for p in self.parameters():
+            dist.broadcast(p.data, src=src, group=self._group)
+        self.__dict__.pop("_memo_store", None)
         n = torch.tensor([float(self.Y.shape[0])], dtype=torch_dtype, device=self.compute_device)
         dist.all_reduce(n, group=self._group)
         self._num_data_global = int(n.item())
@@ -248,8 +257,12 @@ class SVGP(_InducingPointsGP):
         chol_kuu = cholesky(self.kernel.K(self.Z))
         beta, t, L_S = self._whitened(chol_kuu)
         f_mean, f_var = self._predict(x, diag=True, chol_kuu=chol_kuu, _whitened=(beta, t))
-        mll = torch.stack([self.likelihood.expected_log_density(m_i, v_i, y_i)
-                           for m_i, v_i, y_i in zip(f_mean.t(), f_var.t(), y.t())]).sum()
+        if isinstance(self.likelihood, Gaussian):
+            mll = torch.stack([self.likelihood.expected_log_density(m_i, v_i, y_i)
+                               for m_i, v_i, y_i in zip(f_mean.t(), f_var.t(), y.t())]).sum()
+        else:   # the abstract Likelihood API, as the reference calls it (gptorch/models/sparse_gpr.py:274-281)
+            mll = torch.stack([self.likelihood.propagate_log(torch.distributions.Normal(m_i, torch.sqrt(v_i)), y_i)
+                               for m_i, v_i, y_i in zip(f_mean.t(), f_var.t(), y.t())]).sum()
         batch = x.shape[0]
         world = 1
         if self._group is not None:

@@ -315,3 +315,22 @@ def gpr_loss_and_grads(kind, X, Y, ell, variance, noise):
     loss.sum().backward()
     return loss.detach(), {"variance": h.raw_var.grad.clone(), "length_scales": h.raw_ell.grad.clone(),
                            "noise": h.raw_noise.grad.clone()}
+
+
+# --------------------------------------------------------------------------------------------------------
+# seeded helpers of the large pins (tests/golden/large_cases.npz)
+# --------------------------------------------------------------------------------------------------------
+def seeded_q(m, dy, seed=4321):
+    """q(u) for the SVGP pin: mean ~ 0.3 N(0,1); raw Cholesky factor = strictly-lower 0.02 N(0,1) with a raw
+    (log) diagonal of -1 + 0.1 N(0,1).  Used by oracle/make_golden_large.py and by the tests."""
+    g = torch.Generator().manual_seed(seed)
+    q_mu = 0.3 * torch.randn(m, dy, generator=g, dtype=torch.float64)
+    raw = torch.tril(0.02 * torch.randn(m, m, generator=g, dtype=torch.float64), -1)
+    raw = raw + torch.diag(-1.0 + 0.1 * torch.randn(m, generator=g, dtype=torch.float64))
+    return q_mu, raw
+
+
+def projections(G, seed=99, k=8):
+    g = torch.Generator().manual_seed(seed)
+    V = torch.randn(G.shape[1], k, generator=g, dtype=torch.float64).numpy()
+    return np.asarray(G) @ V

@@ -246,6 +246,99 @@ def test_svgp_reference_known_answer(fixtures):
     assert cov.detach().cpu().numpy() == pytest.approx(exp_s)
 
 
+def test_vfe_named_size_pin_n100000_m1024():
+    """BASELINE.md section 3's VFE pin (N = 1e5, D = 16, M = 1024 -> 383333.82272224966) and every gradient of the
+    unmodified reference at that size (oracle/make_golden_large.py)."""
+    from conftest import Cases
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import VFE
+    c, nm = Cases("large_cases.npz"), "vfe_n100000_m1024"
+    assert abs(c.get(nm, "loss").item() - 383333.82272224966) <= 1e-12 * 383333.8
+    X, Y, g = O.synth_regression(100000, 16)
+    Z = O.synth_inducing(X, 1024, g)
+    model = VFE(X.numpy(), Y.numpy(), kernels.Rbf(16, ARD=True), inducing_points=Z.numpy(),
+                likelihood=likelihoods.Gaussian(variance=0.01))
+    loss = model.loss()
+    loss.backward()
+    gr = _grads(model)
+    assert rel_err(loss.item(), 383333.82272224966) <= LML_TOL
+    assert rel_err(gr["kernel.variance"], c.get(nm, "g_variance")) <= GRAD_TOL
+    assert rel_err(gr["kernel.length_scales"], c.get(nm, "g_length_scales")) <= GRAD_TOL
+    assert rel_err(gr["likelihood.variance"], c.get(nm, "g_noise")) <= GRAD_TOL
+    assert rel_err(gr["Z"], c.get(nm, "g_Z")) <= GRAD_TOL
+
+
+def test_svgp_named_size_pin_m2048_b16384():
+    """SVGP Matern52-ARD at configs[3]'s M = 2048, D = 32 on a minibatch of 16384: loss and every gradient of the
+    unmodified reference; the M x M gradient of the raw Cholesky factor through its diagonal, 8 seeded projections
+    and its Frobenius norm."""
+    from conftest import Cases
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import SVGP
+    c, nm = Cases("large_cases.npz"), "svgp_m2048_b16384"
+    n, d, m, batch = 65536, 32, 2048, 16384
+    X, Y, g = O.synth_regression(n, d)
+    Z = O.synth_inducing(X, m, g)
+    idx = torch.randperm(n, generator=g)[:batch]
+    np.random.seed(0)
+    model = SVGP(X.numpy(), Y.numpy(), kernels.Matern52(d, ARD=True), inducing_points=Z.numpy(),
+                 likelihood=likelihoods.Gaussian(variance=0.01), batch_size=batch)
+    q_mu, raw = O.seeded_q(m, 1)
+    model.induced_output_mean.data.copy_(q_mu)
+    model.induced_output_chol_cov.data.copy_(raw)
+    loss = model.loss(X[idx].cuda(), Y[idx].cuda())
+    loss.backward()
+    gr = _grads(model)
+    assert rel_err(loss.item(), c.get(nm, "loss")) <= LML_TOL
+    assert rel_err(gr["kernel.variance"], c.get(nm, "g_variance")) <= GRAD_TOL
+    assert rel_err(gr["kernel.length_scales"], c.get(nm, "g_length_scales")) <= GRAD_TOL
+    assert rel_err(gr["likelihood.variance"], c.get(nm, "g_noise")) <= GRAD_TOL
+    assert rel_err(gr["Z"], c.get(nm, "g_Z")) <= GRAD_TOL
+    assert rel_err(gr["induced_output_mean"], c.get(nm, "g_q_mu")) <= GRAD_TOL
+    G = gr["induced_output_chol_cov"]
+    assert rel_err(np.diag(G), c.get(nm, "g_q_sqrt_raw_diag")) <= GRAD_TOL
+    assert rel_err(O.projections(G), c.get(nm, "g_q_sqrt_raw_proj")) <= GRAD_TOL
+    assert abs(np.linalg.norm(G) - c.get(nm, "g_q_sqrt_raw_fro").item()) <= GRAD_TOL * c.get(nm, "g_q_sqrt_raw_fro").item()
+
+
+def test_svgp_bound_with_a_custom_likelihood_uses_propagate_log():
+    """Only the package's Gaussian has expected_log_density; any other Likelihood subclass goes through the abstract
+    propagate_log(Normal(mean, sqrt(var)), y) exactly as the reference calls it (gptorch/models/sparse_gpr.py:274-281)."""
+    from gptorch_b200 import kernels, likelihoods
+    from gptorch_b200.models import SVGP
+
+    class Wrapped(likelihoods.Likelihood):
+        def __init__(self):
+            super().__init__()
+            self.inner = likelihoods.Gaussian(variance=0.3)
+            self.calls = 0
+
+        def predict_mean_variance(self, mean_f, var_f):
+            return self.inner.predict_mean_variance(mean_f, var_f)
+
+        def propagate_log(self, qf, targets):
+            self.calls += 1
+            assert isinstance(qf, torch.distributions.Normal)
+            return self.inner.propagate_log(qf, targets)
+
+    rng = np.random.RandomState(3)
+    x, y, z = rng.rand(120, 2), rng.rand(120, 2), rng.rand(9, 2)
+    np.random.seed(0)
+    a = SVGP(x, y, kernels.Matern32(2), inducing_points=z, likelihood=likelihoods.Gaussian(variance=0.3))
+    np.random.seed(0)
+    lik = Wrapped()
+    b = SVGP(x, y, kernels.Matern32(2), inducing_points=z, likelihood=lik)
+    b.induced_output_mean.data.copy_(a.induced_output_mean.data)
+    b.induced_output_chol_cov.data.copy_(a.induced_output_chol_cov.data)
+    la, lb = a.loss(), b.loss()
+    assert lik.calls == 2                                   # one per output dimension
+    assert lb.item() == pytest.approx(la.item(), rel=1e-12)
+    lb.backward()
+    assert lik.inner.variance.grad is not None
+
+
 def test_jitter_schedule_matches_reference():
     """functions.cholesky: un-jittered try, then +1e-10 ... ; -I never succeeds (SURVEY 10 'Jitter')."""
     from gptorch_b200 import functions

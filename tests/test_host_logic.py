@@ -172,3 +172,36 @@ def test_host_batch_stream_sequence_matches_the_rng_stream():
     from gptorch_b200.models import sparse_gpr as sg
     big = draw_minibatch_indices(sg.MINIBATCH_PERMUTE_MAX + 5, 1000)
     assert len(set(big.tolist())) == 1000 and big.max() < sg.MINIBATCH_PERMUTE_MAX + 5
+
+
+def test_prediction_memo_key_sees_layout_structure_and_data_changes():
+    """GPModel._memo (the factor cache of _predict) must recompute when the view layout, a sub-module, the parameter
+    values or the data change -- including edits through `.data` that bump no version counter -- and must hit only for
+    the very same tensors in the very same state."""
+    model = GPR(np.random.rand(40, 2), np.random.rand(40, 1), kernels.Rbf(2), likelihood=likelihoods.Gaussian(0.1))
+    calls = []
+
+    def compute():
+        calls.append(1)
+        return len(calls)
+
+    X = model.X
+    with torch.no_grad():
+        assert model._memo("k", X, compute) == 1
+        assert model._memo("k", X, compute) == 1                       # hit: same tensors, same state
+        a, b = X[:10], X[::2][:10]                                     # same data_ptr and shape, different strides
+        assert a.data_ptr() == b.data_ptr() and a.shape == b.shape
+        assert model._memo("k", a, compute) == 2
+        assert model._memo("k", b, compute) == 3
+        assert model._memo("k", X, compute) == 4
+        model.kernel = kernels.Matern32(2)                             # same parameter values, different module
+        assert model._memo("k", X, compute) == 5
+        assert model._memo("k", X, compute) == 5
+        model.kernel.variance.data.add_(0.5)                           # parameter edit through .data
+        assert model._memo("k", X, compute) == 6
+        model.Y = model.Y.clone()                                      # new target tensor with equal values
+        assert model._memo("k", X, compute) == 7
+        model.X.add_(1.0)                                              # in-place edit (bumps the version counter)
+        assert model._memo("k", X, compute) == 8
+    assert model._memo("k", X, compute) == 9                           # autograd enabled: never cached
+    assert model._memo("k", X, compute) == 10

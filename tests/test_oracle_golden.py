@@ -170,3 +170,27 @@ def test_composite_kernels_match_reference(name):
     alpha = O.tri_solve(Y, L)
     loss = 0.5 * alpha.pow(2).sum() + O.tri_logdet(L) + 0.5 * n * np.log(2 * np.pi)
     assert rel_err(loss.numpy(), c.get(name, "loss")) < 1e-12
+
+
+def test_oracle_reproduces_the_named_size_vfe_pin():
+    """VFE N = 1e5, D = 16, M = 1024 -> 383333.82272224966, and the reference's gradients at
+    that size (tests/golden/large_cases.npz, oracle/make_golden_large.py)."""
+    c, nm = Cases("large_cases.npz"), "vfe_n100000_m1024"
+    X, Y, g = O.synth_regression(100000, 16)
+    Z = O.synth_inducing(X, 1024, g).requires_grad_(True)
+    h = O.Hyper("Rbf", np.ones(16), 1.0, 0.01)
+    loss = -O.vfe_elbo(h, X, Y, Z)
+    loss.backward()
+    assert abs(loss.item() - 383333.82272224966) <= 1e-10 * 383333.8
+    assert rel_err(loss.item(), c.get(nm, "loss")) <= 1e-12
+    assert rel_err(h.raw_ell.grad.numpy(), c.get(nm, "g_length_scales")) <= 1e-9
+    assert rel_err(h.raw_var.grad.numpy(), c.get(nm, "g_variance")) <= 1e-9
+    assert rel_err(h.raw_noise.grad.numpy(), c.get(nm, "g_noise")) <= 1e-9
+    assert rel_err(Z.grad.numpy(), c.get(nm, "g_Z")) <= 1e-9
+
+
+def test_large_gpr_fixtures_carry_the_survey_loss_pins():
+    c = Cases("large_cases.npz")
+    assert c.get("gpr_n8192", "loss").item() == pytest.approx(-6511.334472842767, rel=1e-13)
+    assert c.get("gpr_n16384", "loss").item() == pytest.approx(-13224.865836863326, rel=1e-13)
+    assert c.get("gpr_n16384", "g_length_scales").shape == (8,)
