@@ -78,6 +78,24 @@ class KernelFn(Function):
         return None, gX, gX2, g_ell, g_s2, g_noise
 
 
+class LinearKdiagFn(Function):
+    """Linear.Kdiag (gptorch/kernels.py:264-265): out[i] = sum_d v_d x_id^2 in one pass over X (gpb_linear_kdiag).
+    The backward is an O(n D) element-wise product, left to torch."""
+
+    @staticmethod
+    def forward(ctx, X, v):
+        ctx.save_for_backward(X, v)
+        return nv.linear_kdiag(X, v)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        X, v = ctx.saved_tensors
+        gX = (2.0 * g[:, None]) * X * v if ctx.needs_input_grad[0] else None
+        gv = (g[:, None] * X * X).sum(0).reshape(v.shape) if ctx.needs_input_grad[1] else None
+        return gX, gv
+
+
 def _spec_terms(spec, params):
     """Resolve a composite spec -- terms of (kind, ell index or -1, sigma2 index or -1) -- against `params`."""
     return [[(k, params[ie] if ie >= 0 else None, params[isg] if isg >= 0 else None) for (k, ie, isg) in term]

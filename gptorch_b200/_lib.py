@@ -28,6 +28,7 @@ SIGNATURES = {
     "gpb_block_size": (c_int, []),
     "gpb_launch_count": (c_long, []),
     "gpb_reset_launch_count": (None, []),
+    "gpb_dmma_issue_probe": (c_int, [c_int, c_void_p, c_size_t, ctypes.POINTER(c_double), c_void_p]),
     "gpb_kern_fwd": (c_int, [c_int, c_void_p, c_int, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_int,
                              c_void_p, c_void_p, c_int, c_void_p, c_long, c_void_p]),
     "gpb_kern_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

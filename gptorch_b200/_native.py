@@ -93,6 +93,25 @@ def launch_count():
 def reset_launch_count():
     _lib.load().gpb_reset_launch_count()
 
+def dmma_issue_peak_tflops(iters=20000, repeats=5):
+    """FP64 DMMA issue-rate ceiling of the current device, measured live (gpb_dmma_issue_probe, CUDA events, best
+    of `repeats` after one warm-up launch)."""
+    import ctypes
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    scratch = torch.empty(2 * sms * 512, dtype=torch.float64, device="cuda")
+    flop = ctypes.c_double(0.0)
+    best = float("inf")
+    for i in range(repeats + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("gpb_dmma_issue_probe", int(iters), ptr(scratch), scratch.numel() * 8, ctypes.byref(flop), stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = min(best, e0.elapsed_time(e1))
+    return flop.value / best / 1e9
+
+
 KIND = {"Rbf": 0, "SquaredExponential": 0, "Exp": 1, "Matern12": 1, "Matern32": 2, "Matern52": 3, "Linear": 4,
         "Periodic": 5, "Constant": 6, "Bias": 6, "White": 7}
 KERN_LINEAR, KERN_CONSTANT, KERN_WHITE = 4, 6, 7

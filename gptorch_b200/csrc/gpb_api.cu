@@ -51,6 +51,23 @@ int gpr_grad(int kind, const double* X, int n, long ldx, int D, const double* el
 using namespace gpb;
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
+// FP64 tensor-pipe issue-rate probe: every warp issues independent DMMA.8x8x4 chains from registers, nothing else.
+// This is the ceiling the GEMM engine is measured against (bench.py roofline.peak).
+__global__ void __launch_bounds__(512) dmma_issue_probe_kernel(double* out, int iters) {
+  double c[8][2];
+  double a = threadIdx.x * 1e-9, b = 1.0 + threadIdx.x * 1e-9;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = -i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma884_ordered(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -58,6 +75,18 @@ int gpb_version(void) { return 100; }
 const char* gpb_last_error(void) { return last_error(); }
 int gpb_block_size(void) { return NB; }
 long gpb_launch_count(void) { return launch_count(); }
+int gpb_dmma_issue_probe(int iters, double* scratch, size_t scratch_bytes, double* flop_out, void* stream) {
+  int dev = 0, sms = 0;
+  GPB_CUDA_CHECK(cudaGetDevice(&dev));
+  GPB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = 2 * sms, threads = 512;
+  if (iters <= 0 || scratch == nullptr || scratch_bytes < sizeof(double) * blocks * threads) return GPB_ERR_BADARG;
+  dmma_issue_probe_kernel<<<blocks, threads, 0, S(stream)>>>(scratch, iters);
+  GPB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  if (flop_out) *flop_out = (double)blocks * (threads / 32) * (double)iters * 8.0 * (8 * 8 * 4 * 2.0);
+  return GPB_OK;
+}
 void gpb_reset_launch_count(void) { reset_launch_count(); }
 
 int gpb_kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,

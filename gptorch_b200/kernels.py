@@ -167,6 +167,8 @@ class Linear(Kernel):
                                  self.variance.transform(), None)
 
     def Kdiag(self, X):
+        if X.is_cuda:       # gpb_linear_kdiag; host tensors keep the composite (Kdiag of a CPU tensor needs no kernel)
+            return ag.LinearKdiagFn.apply(_f64(X), self.variance.transform())
         return torch.sum(X * X * self.variance.transform(), 1)
 
 

@@ -119,6 +119,9 @@ class NativeOps:
         return g_ell, g_s2
 
 
+WAIT_LOG = None   # set to a list by bench.py to collect (start, end) events around every wait for a panel
+
+
 class _Pipeline:
     """Double-buffered panel exchange: panel p + 1 is staged and broadcast on a side stream while the main stream
     works with panel p.  On a CPU device (gloo tests) everything is issued in order on the host."""
@@ -154,7 +157,14 @@ class _Pipeline:
 
     def acquire(self, k):
         if self.cuda and self.ready[k] is not None:
-            self.main.wait_event(self.ready[k])
+            if WAIT_LOG is None:
+                self.main.wait_event(self.ready[k])
+            else:   # bench.py: how long the main stream stalls for the next panel (factor chain + broadcast)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.main)
+                self.main.wait_event(self.ready[k])
+                e1.record(self.main)
+                WAIT_LOG.append((e0, e1))
 
     def release(self, k):
         if self.cuda:

@@ -56,6 +56,12 @@ int gpb_block_size(void);
 /* Number of CUDA kernels this library has launched since load / the last reset (bench.py: gpu_launches). */
 long gpb_launch_count(void);
 void gpb_reset_launch_count(void);
+/* Measurement aid (bench.py roofline.peak): one launch in which every warp of 2 CTAs x 16 warps per SM issues
+ * independent DMMA.8x8x4 chains from registers for `iters` rounds of 8 -- the FP64 tensor-pipe issue ceiling the GEMM
+ * engine is bounded by (torch's cuBLAS DGEMM is the other, lower, denominator).  `scratch`: device buffer of at least
+ * 2 * SMs * 512 doubles; *flop_out (host, optional) receives the flop count of the launch; the caller times it with
+ * CUDA events on `stream`.  No reference counterpart. */
+int gpb_dmma_issue_probe(int iters, double* scratch, size_t scratch_bytes, double* flop_out, void* stream);
 
 /* ---- covariance construction ---------------------------------------------------------------------------
  * K[i][j] = k(X[i,:], X2[j,:]).  Replaces Kernel.K(X, X2) (gptorch/kernels.py:189,198,205,220,258) with its

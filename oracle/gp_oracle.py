@@ -87,9 +87,33 @@ def scaled_r2(X, X2, ell):
     return sqdist(X / ell) if X2 is None else sqdist(X / ell, X2 / ell)
 
 
+_EXACT_DIAGONAL = False
+
+
+class exact_diagonal:
+    """Context manager: a CHECKER VARIANT, not the reference.  Inside it the scaled distance of K(X) (X2 None) is
+    exactly 0 on the diagonal (value and gradient) instead of sqrt(round-off of |x|^2 + |x|^2 - 2 x.x) ~ 1e-8.
+    It isolates the one documented deviation of the CUDA kernels from the reference (Exp/Matern12):
+    everything else in the oracle stays the reference's arithmetic.  oracle/exact_witness.py (mpmath) shows which of
+    the two diagonals is the mathematically right one."""
+
+    def __enter__(self):
+        global _EXACT_DIAGONAL
+        self.prev, _EXACT_DIAGONAL = _EXACT_DIAGONAL, True
+        return self
+
+    def __exit__(self, *exc):
+        global _EXACT_DIAGONAL
+        _EXACT_DIAGONAL = self.prev
+        return False
+
+
 def scaled_r(X, X2, ell):
     """gptorch/kernels.py:161-172."""
-    return torch.sqrt(torch.clamp(scaled_r2(X, X2, ell), min=1e-40))
+    r = torch.sqrt(torch.clamp(scaled_r2(X, X2, ell), min=1e-40))
+    if _EXACT_DIAGONAL and X2 is None:
+        r = r * (1.0 - torch.eye(X.shape[0], dtype=DTYPE))
+    return r
 
 
 def cov(kind, X, X2, ell, variance):

@@ -24,7 +24,8 @@ typedef int (*potrf_fn)(double*, int, long, double*, int*, void*);
 
 int main(int argc, char** argv) {
   static const char* names[] = {
-      "gpb_version", "gpb_last_error", "gpb_block_size", "gpb_launch_count", "gpb_reset_launch_count", "gpb_kern_fwd",
+      "gpb_version", "gpb_last_error", "gpb_block_size", "gpb_launch_count", "gpb_reset_launch_count",
+      "gpb_dmma_issue_probe", "gpb_kern_fwd",
       "gpb_kern_bwd_workspace_bytes", "gpb_kern_bwd", "gpb_kern_bwd_mul", "gpb_kern_sop_fwd", "gpb_linear_kdiag",
       "gpb_potrf_lower", "gpb_tri_diag_inverse", "gpb_potri_workspace_bytes", "gpb_potri_lower", "gpb_trtri_upper",
       "gpb_potri_assemble", "gpb_tri_zero_upper", "gpb_add_diag", "gpb_trsv_workspace_bytes", "gpb_trsv_lower",

@@ -44,15 +44,42 @@ def test_gpr_loss_grad_predict(name):
     assert loss.is_cuda and loss.ndimension() == 1          # test/test_models/test_gpr.py:42
     loss.backward()
     gr = _grads(model)
-    # Exp/Matern12 only: the reference's K(X) diagonal is sigma2*exp(-sqrt(round-off of |x|^2+|x|^2-2x.x)) ~
-    # sigma2*(1 - 1e-8), i.e. it carries O(1e-8) noise that depends on MKL's summation order; the CUDA
-    # path uses the exact r=0 there.  Parity for this kernel is therefore bounded by the reference's noise floor.
-    ltol = LML_TOL if kind != "Exp" else 2e-7
-    assert rel_err(loss.detach().cpu().numpy(), c.get(name, "loss")) <= ltol
-    gtol = GRAD_TOL if kind != "Exp" else 5e-6
-    assert rel_err(gr["kernel.variance"], c.get(name, "g_variance")) <= gtol
-    assert rel_err(gr["kernel.length_scales"], c.get(name, "g_length_scales")) <= gtol
-    assert rel_err(gr["likelihood.variance"], c.get(name, "g_noise")) <= gtol
+    lo, g_var, g_ell, g_noise = (loss.detach().cpu().numpy(), gr["kernel.variance"], gr["kernel.length_scales"],
+                                 gr["likelihood.variance"])
+    if kind != "Exp":
+        assert rel_err(lo, c.get(name, "loss")) <= LML_TOL
+        assert rel_err(g_var, c.get(name, "g_variance")) <= GRAD_TOL
+        assert rel_err(g_ell, c.get(name, "g_length_scales")) <= GRAD_TOL
+        assert rel_err(g_noise, c.get(name, "g_noise")) <= GRAD_TOL
+    else:
+        # Exp/Matern12: the ONE documented deviation.  The reference's K(X) diagonal is
+        # sigma2 * exp(-sqrt(round-off of |x|^2 + |x|^2 - 2 x.x)) ~ sigma2 (1 - 1e-8): noise that depends on the BLAS
+        # summation order (the reference's CPU and CUDA paths differ from each other by 2.6e-9 .. 5.9e-9 on the LML,
+        # profiles/r02_reference_box.json); the CUDA kernel uses the exact r = 0 there.  Proven, not assumed:
+        # (1) against the oracle with that single change (O.exact_diagonal) the north-star tolerances hold,
+        # (2) against the reference's golden the distance is bounded by the reference's own distance from (1).
+        from oracle import gp_oracle as O
+        with O.exact_diagonal():
+            e_loss, e_gr = O.gpr_loss_and_grads(kind, X, Y, c.get(name, "ell"), float(c.get(name, "variance")),
+                                                float(c.get(name, "noise")))
+        assert rel_err(lo, e_loss.numpy()) <= LML_TOL
+        assert rel_err(g_var, e_gr["variance"].numpy()) <= GRAD_TOL
+        assert rel_err(g_ell, e_gr["length_scales"].numpy()) <= GRAD_TOL
+        assert rel_err(g_noise, e_gr["noise"].numpy()) <= GRAD_TOL
+        assert rel_err(lo, c.get(name, "loss")) <= LML_TOL + rel_err(e_loss.numpy(), c.get(name, "loss"))
+        assert rel_err(g_ell, c.get(name, "g_length_scales")) <= GRAD_TOL + rel_err(e_gr["length_scales"].numpy(), c.get(name, "g_length_scales"))
+        assert rel_err(g_noise, c.get(name, "g_noise")) <= GRAD_TOL + rel_err(e_gr["noise"].numpy(), c.get(name, "g_noise"))
+        if X.shape[0] <= 128:
+            # (3) a 40-digit mpmath evaluation (oracle/exact_witness.py): the CUDA result is within tolerance of the
+            # exact value while the reference is NOT -- the exception is the reference's noise floor, not ours.
+            from oracle import exact_witness as W
+            w_loss, w_gr = W.gpr_loss_and_grads(kind, c.get(name, "X"), c.get(name, "Y"), c.get(name, "ell"),
+                                                float(c.get(name, "variance")), float(c.get(name, "noise")))
+            assert rel_err(lo, w_loss) <= LML_TOL
+            assert rel_err(g_var, w_gr["variance"]) <= GRAD_TOL
+            assert rel_err(g_ell, w_gr["length_scales"]) <= GRAD_TOL
+            assert rel_err(g_noise, w_gr["noise"]) <= GRAD_TOL
+            assert rel_err(c.get(name, "loss"), w_loss) > LML_TOL > rel_err(lo, w_loss)
     # loss(x=, y=) equals loss() (test/test_models/test_gpr.py:45-47)
     assert model.loss(x=model.X, y=model.Y).item() == pytest.approx(loss.item(), rel=1e-13)
     if c.has(name, "Xs"):
@@ -491,7 +518,7 @@ def test_distributed_gpr_loss_and_gradient(n, panel):
     owner); loss and all hyper-parameter gradients must match the single-GPU fused node."""
     import socket
     import torch.multiprocessing as mp
-    world = min(torch.cuda.device_count(), 2)
+    world = min(torch.cuda.device_count(), 8)       # every visible GPU is a rank (8 on the full box)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]

@@ -194,3 +194,28 @@ def test_large_gpr_fixtures_carry_the_survey_loss_pins():
     assert c.get("gpr_n8192", "loss").item() == pytest.approx(-6511.334472842767, rel=1e-13)
     assert c.get("gpr_n16384", "loss").item() == pytest.approx(-13224.865836863326, rel=1e-13)
     assert c.get("gpr_n16384", "g_length_scales").shape == (8,)
+
+
+@pytest.mark.parametrize("kind", ["Exp", "Matern32"])
+def test_high_precision_witness_locates_the_exp_noise_floor(kind):
+    """oracle/exact_witness.py (mpmath, 40 digits) against the reference's golden and the oracle on a 96-point case:
+    for Matern32 all three agree to round-off; for Exp the REFERENCE is 1e-8 away from the exact value (its K(X)
+    diagonal is sigma2 * exp(-sqrt(round-off)), gptorch/util.py:73-88 + gptorch/kernels.py:171-172) while the oracle
+    with the exact diagonal -- what the CUDA kernels compute -- agrees with the exact value to round-off."""
+    from oracle import exact_witness as W
+    c, nm = _GPR, "gpr_%s_n96_d3_default" % kind
+    X, Y = c.get(nm, "X"), c.get(nm, "Y")
+    args = (c.get(nm, "ell"), float(c.get(nm, "variance")), float(c.get(nm, "noise")))
+    w_loss, w_gr = W.gpr_loss_and_grads(kind, X, Y, *args)
+    with O.exact_diagonal():
+        e_loss, e_gr = O.gpr_loss_and_grads(kind, T(X), T(Y), *args)
+    assert rel_err(e_loss.numpy(), w_loss) < 1e-12
+    assert rel_err(e_gr["length_scales"].numpy(), w_gr["length_scales"]) < 1e-11
+    assert rel_err(e_gr["variance"].numpy(), w_gr["variance"]) < 1e-11
+    assert rel_err(e_gr["noise"].numpy(), w_gr["noise"]) < 1e-11
+    ref_dev = rel_err(c.get(nm, "loss"), w_loss)
+    if kind == "Exp":
+        assert 1e-9 < ref_dev < 1e-6
+        assert rel_err(c.get(nm, "g_noise"), w_gr["noise"]) > 1e-9
+    else:
+        assert ref_dev < 1e-12
