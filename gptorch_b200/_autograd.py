@@ -379,7 +379,7 @@ class GemmFn(Function):
 # fused GPR log marginal likelihood
 # ------------------------------------------------------------------------------------------------------
 JITTER_TRIES = 10  # gptorch/functions.py:21
-VFE_PANEL_CACHE_BYTES = 48 << 30   # keep A^T panels for backward up to this size (B200: 180 GB HBM)
+VFE_PANEL_CACHE_BYTES = 8 << 30    # reference-order VFE: keep the solved A^T panels for backward up to this size
 VFE_SPLITS = 16    # k-slices of the streamed Gram products (fills the GPU when M x M has few tiles)
 
 
@@ -501,18 +501,47 @@ class GPRCompositeLogLikFn(Function):
 # ------------------------------------------------------------------------------------------------------
 # VFE sufficient statistics, streamed over row chunks of X
 # ------------------------------------------------------------------------------------------------------
+def kuu_condition_estimate(L, T, iters=8):
+    """Estimate of cond_2(Kuu) = lambda_max(L L^T) * lambda_max(T T^T) (T = L^-T) by two short power iterations on the
+    native matrix-vector kernel.  Power iteration approaches each factor from below, so the result is a (slightly low)
+    estimate; callers compare it with a threshold that leaves a safety margin."""
+    m = L.shape[0]
+    Lt, Tt = L.t().contiguous(), T.t().contiguous()
+    out = []
+    for A, At in ((L, Lt), (T, Tt)):                 # v <- A (A^T v)
+        v = torch.full((m, 1), 1.0 / math.sqrt(m), dtype=torch.float64, device=L.device)
+        u = torch.empty_like(v)
+        lam = None
+        for _ in range(iters):
+            nv.gemv_t(A, v, u, beta=0.0)            # u = A^T v
+            nv.gemv_t(At, u, v, beta=0.0)           # v = A u
+            lam = torch.linalg.vector_norm(v)
+            v = v / lam
+        out.append(lam)
+    return float((out[0] * out[1]).item())
+
+
 class VfeStatsFn(Function):
     """(A A^T, A Y) with A = L^-1 Kuf (gptorch/models/sparse_gpr.py:127-137) without ever holding Kuf.
 
-    Rows of X are processed in chunks: Kfu_c = K(X_c, Z) -> At_c = Kfu_c L^-T -> AA += At_c^T At_c,
-    AY += At_c^T Y_c (the reference's order of operations: solve first, then the Gram product).  backward
-    re-streams the chunks: G_c = At_c (S L^-1) + Y_c (L^-T gAY)^T with S = gAA + gAA^T, reduced against
-    dK/d(ell, sigma2, Z) by gpb_kern_bwd.  With torch.distributed initialised and `group` given, rows are this
-    rank's shard and the two statistics / the streamed gradients are all-reduced.
+    Rows of X are processed in chunks.  Two forms, selected by `phi_form`:
+
+    * reference order (phi_form False): Kfu_c = K(X_c, Z) -> At_c = Kfu_c L^-T -> AA += At_c^T At_c, AY += At_c^T Y_c --
+      solve first, then the Gram product, exactly the reference's sequence of roundings; 5 N M^2 flop per loss+grad.
+    * Phi form (phi_form True): Phi += Kfu_c^T Kfu_c, psi += Kfu_c^T Y_c over the stream, then the M x M congruence
+      AA = L^-1 Phi L^-T, AY = L^-1 psi once -- 3 N M^2 flop per loss+grad (SURVEY 8d's algorithmic count), no solved
+      panels to keep or rebuild for the backward pass.  The congruence amplifies the rounding of Phi by cond(Kuu)
+      (normal-equations effect; the reference order only by its square root), so the caller enables it only when the
+      estimated cond_2(Kuu) keeps the error far inside the parity tolerances (VFE._stats, settings.vfe_phi_form).
+
+    backward re-streams the chunks: the gradient with respect to a panel is G_c = At_c (S L^-1) + Y_c (L^-T gAY)^T
+    (reference order) or G_c = Kfu_c (L^-T S L^-1) + Y_c (L^-T gAY)^T (Phi form), S = gAA + gAA^T, reduced against
+    dK/d(ell, sigma2, Z) by gpb_kern_bwd.  With torch.distributed initialised and `group` given, rows are this rank's
+    shard and the M x M statistics / the streamed gradients are all-reduced.
     """
 
     @staticmethod
-    def forward(ctx, kind, X, Y, Z, ell, sigma2, L, chunk, group):
+    def forward(ctx, kind, X, Y, Z, ell, sigma2, L, chunk, group, phi_form=False):
         X, Y, Z = nv._c(X), nv._c(Y), nv._c(Z)
         Lc = nv._gemm_operand(L)
         dinv = _dinv_of(L)
@@ -524,18 +553,19 @@ class VfeStatsFn(Function):
         ldm = m + (m & 1)
         AA3 = torch.zeros((VFE_SPLITS, m, ldm), dtype=torch.float64, device=X.device)
         AYf = torch.zeros((m, dy), dtype=torch.float64, device=X.device)
-        # Keep the solved panels A^T for the backward pass when they fit the budget (N*M*8 bytes); otherwise the
-        # backward pass re-streams them from X (one more covariance build + solve per chunk).
-        keep = any(ctx.needs_input_grad) and n * ldm * 8 <= VFE_PANEL_CACHE_BYTES
+        # Reference order only: keep the solved panels A^T for the backward pass when they fit a small budget
+        # (N*M*8 bytes); otherwise the backward pass rebuilds them (one more covariance build + solve per chunk).
+        keep = (not phi_form) and any(ctx.needs_input_grad) and n * ldm * 8 <= VFE_PANEL_CACHE_BYTES
         cache = []
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            At, ldat = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, T)
+            P = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, None if phi_form else T)
             if keep:
-                cache.append(At)
+                cache.append(P)
             with nv.phase("vfe_gram"):
-                nv.gemm_splitk(nv.GEMM_TN, At, At, kper, AA3, beta=1.0, lower_only=True)
-                nv.gemv_t(At, Y[s:e], AYf, beta=1.0)
+                nv.gemm_splitk(nv.GEMM_TN, P, P, kper, AA3, beta=1.0, lower_only=True)
+                nv.gemv_t(P, Y[s:e], AYf, beta=1.0)
+            del P
         AAf = AA3.sum(0)[:, :m]
         AAf = torch.tril(AAf) + torch.tril(AAf, -1).t()
         # sum_i k(x_i, x_i) = n * sigma2 for a stationary kernel (gptorch/kernels.py:174-179); sum Y^2
@@ -544,7 +574,13 @@ class VfeStatsFn(Function):
             torch.distributed.all_reduce(AAf, group=group)
             torch.distributed.all_reduce(AYf, group=group)
             torch.distributed.all_reduce(scal, group=group)
-        ctx.kind, ctx.chunk, ctx.group, ctx.n_local = kind, chunk, group, n
+        if phi_form:
+            with nv.phase("vfe_congruence"):
+                PhiT = nv.gemm(nv.GEMM_NN, AAf, T, flags=nv.GF_KHI_N)          # Phi L^-T  (T upper: k <= n)
+                AAf = nv.gemm(nv.GEMM_TN, T, PhiT, flags=nv.GF_KHI_M)          # L^-1 Phi L^-T
+                AAf = 0.5 * (AAf + AAf.t())
+                AYf = nv.gemm(nv.GEMM_TN, T, AYf, flags=nv.GF_KHI_M)           # L^-1 psi
+        ctx.kind, ctx.chunk, ctx.group, ctx.n_local, ctx.phi_form = kind, chunk, group, n, bool(phi_form)
         ctx.panels = cache if keep else None
         ctx.save_for_backward(X, Y, Z, ell, sigma2, T, AAf, AYf)
         return AAf, AYf, scal[0], scal[1]
@@ -556,23 +592,27 @@ class VfeStatsFn(Function):
 
     @staticmethod
     def _panel(kind, Xc, Z, ell, sigma2, T):
-        """A^T = K(Xc, Z) L^-T for one row chunk, as ONE product with the dense upper-triangular T = L^-T (k <= n):
-        every output tile is written once with k up to M, instead of the solve recursion's many short-k passes."""
+        """One row chunk: Kfu_c = K(Xc, Z) (T None) or A_c^T = Kfu_c L^-T as ONE product with the dense upper-triangular
+        T = L^-T (k <= n): every output tile is written once with k up to M, instead of the solve recursion's many
+        short-k passes."""
         with nv.phase("vfe_kern_fwd"):
             Kfu = nv.kern_fwd(kind, Xc, Z, ell, sigma2)
+        if T is None:
+            return Kfu
         with nv.phase("vfe_trsm"):
-            At = nv.gemm(nv.GEMM_NN, Kfu, T, flags=nv.GF_KHI_N)
-        return At, At.stride(0)
+            return nv.gemm(nv.GEMM_NN, Kfu, T, flags=nv.GF_KHI_N)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gAA, gAY, g_kd, _g_yy):
         X, Y, Z, ell, sigma2, T, AA, AY = ctx.saved_tensors
-        kind, chunk, group = ctx.kind, ctx.chunk, ctx.group
+        kind, chunk, group, phi = ctx.kind, ctx.chunk, ctx.group, ctx.phi_form
         n = X.shape[0]
         S = nv._c(gAA + gAA.t())
         gAY = nv._c(gAY)
         R = nv.gemm(nv.GEMM_NT, S, T, flags=nv.GF_KLO_N)   # S L^-1 = S T^T
+        if phi:
+            R = nv.gemm(nv.GEMM_NN, T, R, flags=nv.GF_KLO_M)   # L^-T S L^-1  (T[m][k] = 0 for k < m)
         w = nv.gemm(nv.GEMM_NN, T, gAY)          # L^-T gAY   (m x dy)
         g_ell = torch.zeros_like(ell.reshape(-1))
         g_s2 = torch.zeros(1, dtype=torch.float64, device=X.device)
@@ -581,15 +621,17 @@ class VfeStatsFn(Function):
         for ci, s in enumerate(range(0, n, chunk)):
             e = min(n, s + chunk)
             if panels is not None:
-                At = panels[ci]
+                P = panels[ci]
                 panels[ci] = None
             else:
-                At, _ = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, T)
+                P = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, None if phi else T)
             with nv.phase("vfe_bwd_gemm"):
-                G = nv.gemm(nv.GEMM_NN, At, R)
+                G = nv.gemm(nv.GEMM_NN, P, R)
                 nv.gemm(nv.GEMM_NT, Y[s:e], w, beta=1.0, C=G)
+            del P
             with nv.phase("vfe_kern_bwd"):
                 ge, gs, gz = nv.kern_bwd(kind, X[s:e], Z, ell, sigma2, G, True)
+            del G
             g_ell += ge
             g_s2 += gs
             gZ += gz
@@ -605,4 +647,4 @@ class VfeStatsFn(Function):
         return (None, None, None, gZ if ctx.needs_input_grad[3] else None,
                 g_ell.reshape(ell.shape) if ctx.needs_input_grad[4] else None,
                 g_s2.reshape(sigma2.shape) if (sigma2 is not None and ctx.needs_input_grad[5]) else None,
-                gL if ctx.needs_input_grad[6] else None, None, None)
+                gL if ctx.needs_input_grad[6] else None, None, None, None)

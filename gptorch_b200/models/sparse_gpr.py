@@ -89,11 +89,29 @@ class VFE(_InducingPointsGP):
         kind = _native_kind(self.kernel)
         if kind is not None:
             return ag.VfeStatsFn.apply(kind, x, self.Y, self.Z, self.kernel.length_scales.transform(),
-                                       self.kernel.variance.transform(), L, VFE_CHUNK_ROWS, self._group)
+                                       self.kernel.variance.transform(), L, VFE_CHUNK_ROWS, self._group,
+                                       self._use_phi_form(L, x.shape[0]))
         if self._group is not None:
             raise NotImplementedError("row-sharded VFE needs a stationary kernel")
         At = ag.TrsmRightFn.apply(self.kernel.K(x, self.Z), L, ag._dinv_of(L))
         return mm_tn(At, At), mm_tn(At, self.Y), self.kernel.Kdiag(x).sum(), self.Y.pow(2).sum()
+
+    def _use_phi_form(self, L, rows):
+        """settings.vfe_phi_form: the 3 N M^2 Phi form when Kuu is well enough conditioned (one host read per
+        evaluation; every rank sees the same replicated L and therefore takes the same branch).  "auto" keeps the
+        reference order for short data sets (nothing to gain below 16 M rows per rank; with row sharding all ranks must
+        agree, so the local row count only switches the form off when every rank is short) and while the evaluation is
+        being captured into a CUDA graph (no host reads there)."""
+        mode = settings.vfe_phi_form
+        if mode is True or mode is False:
+            return mode
+        if torch.cuda.is_current_stream_capturing() or (self._group is None and rows < 16 * L.shape[0]):
+            return False
+        with torch.no_grad():
+            Lc = ag.nv._gemm_operand(L.detach())
+            cond = ag.kuu_condition_estimate(Lc, ag._tinv(Lc, ag._dinv_of(L)))
+        self.last_kuu_condition = cond
+        return cond <= settings.vfe_phi_cond_max
 
     def _core(self, x):
         noise = self.likelihood.variance.transform()

@@ -33,3 +33,12 @@ def set_default_device(device):
 # eagerly, ~0.1 ms replayed.  Set to False to force eager evaluation.
 cuda_graphs = True
 graph_max_rows = 4096      # larger evaluations are compute-bound (and use the look-ahead side stream): eager
+
+
+# VFE sufficient statistics (gptorch_b200/_autograd.py VfeStatsFn): "auto" streams Phi = Kuf Kfu and applies L^-1 . L^-T
+# once (3 N M^2 flop per loss+grad instead of the reference order's 5 N M^2) when the estimated cond_2(Kuu) is at most
+# vfe_phi_cond_max -- the congruence amplifies rounding by cond(Kuu); measured against the reference the hyper-parameter
+# gradients deviate by <= 200 * eps * cond (tests/test_gpu_models.py), i.e. <= 1e-8 at the default bound, an order of
+# magnitude inside the 1e-7 tolerance.  False = always the reference's order of operations; True = always the Phi form.
+vfe_phi_form = "auto"
+vfe_phi_cond_max = 2.0e5

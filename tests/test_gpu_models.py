@@ -296,6 +296,78 @@ def test_vfe_named_size_pin_n100000_m1024():
     assert rel_err(gr["Z"], c.get(nm, "g_Z")) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("name", _VFE.names + ["vfe_n100000_m1024"])
+def test_vfe_phi_form_meets_the_parity_tolerances(name):
+    """settings.vfe_phi_form = True (Phi = Kuf Kfu streamed, one M x M congruence; 3 N M^2 flop instead of the reference
+    order's 5 N M^2): loss <= 1e-9 and every gradient <= 1e-7 against the unmodified reference on every VFE golden,
+    including BASELINE.md's N = 1e5 / M = 1024 pin."""
+    from conftest import Cases
+    from oracle import gp_oracle as O
+    from gptorch_b200 import likelihoods, settings
+    from gptorch_b200.models import VFE
+    large = name.startswith("vfe_n100000")
+    c = Cases("large_cases.npz") if large else _VFE
+    if large:
+        X, Y, g = O.synth_regression(100000, 16)
+        Z, kind, d, ell, var, noise = O.synth_inducing(X, 1024, g), "Rbf", 16, np.ones(16), 1.0, 0.01
+    else:
+        X, Y, g = case_inputs(c, name)
+        m = int(c.get(name, "m"))
+        Z = torch.as_tensor(c.get(name, "Z")) if c.has(name, "Z") else O.synth_inducing(X, m, g)
+        kind, d, ell, var, noise = (str(c.get(name, "kind")), int(c.get(name, "d")), c.get(name, "ell"),
+                                    float(c.get(name, "variance")), float(c.get(name, "noise")))
+    model = VFE(X.numpy(), Y.numpy(), _kernel(kind, d, ell, var), inducing_points=Z.numpy(),
+                likelihood=likelihoods.Gaussian(variance=noise))
+    settings.vfe_phi_form = True
+    try:
+        loss = model.loss()
+        loss.backward()
+    finally:
+        settings.vfe_phi_form = "auto"
+    gr = _grads(model)
+    assert rel_err(loss.item(), c.get(name, "loss")) <= LML_TOL
+    assert rel_err(gr["kernel.variance"], c.get(name, "g_variance")) <= GRAD_TOL
+    assert rel_err(gr["kernel.length_scales"], c.get(name, "g_length_scales")) <= GRAD_TOL
+    assert rel_err(gr["likelihood.variance"], c.get(name, "g_noise")) <= GRAD_TOL
+    assert rel_err(gr["Z"], c.get(name, "g_Z")) <= GRAD_TOL
+
+
+def test_vfe_phi_form_is_gated_by_the_conditioning_of_kuu():
+    """"auto": the Phi form is used only when the estimated cond_2(Kuu) is below settings.vfe_phi_cond_max.  The
+    estimate (two power iterations on the native matvec) is checked against the exact condition number; an
+    ill-conditioned Kuu (long length scales) takes the reference order and still matches the oracle."""
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods, settings, _autograd as ag, _native as nv
+    from gptorch_b200.models import VFE
+    n, d, m = 6000, 4, 64
+    X, Y, g = O.synth_regression(n, d)
+    Z = O.synth_inducing(X, m, g)
+    used = []
+    for ell, expect_phi in ((0.4, True), (1.0, False)):
+        model = VFE(X.numpy(), Y.numpy(), kernels.Rbf(d, ARD=True, length_scales=ell * np.ones(d)), inducing_points=Z.numpy(),
+                    likelihood=likelihoods.Gaussian(variance=0.01))
+        assert n >= 16 * m
+        timer = nv.PhaseTimer()
+        nv.install_timer(timer)
+        try:
+            loss = model.loss()
+        finally:
+            nv.install_timer(None)
+        phases = timer.totals_ms()
+        used.append("vfe_congruence" in phases)
+        assert used[-1] == expect_phi and ("vfe_trsm" in phases) == (not expect_phi)
+        Kuu = O.cov("Rbf", Z, None, ell * torch.ones(d, dtype=torch.float64), torch.ones(1, dtype=torch.float64))
+        ev = torch.linalg.eigvalsh(Kuu)
+        exact = float(ev[-1] / ev[0])
+        if exact < 1e12:
+            assert 0.3 * exact <= model.last_kuu_condition <= 1.05 * exact
+        assert (model.last_kuu_condition <= settings.vfe_phi_cond_max) == expect_phi
+        h = O.Hyper("Rbf", ell * np.ones(d), 1.0, 0.01)
+        ref = -O.vfe_elbo(h, X, Y, Z)
+        assert rel_err(loss.item(), ref.item()) <= LML_TOL
+    assert used == [True, False]
+
+
 def test_svgp_named_size_pin_m2048_b16384():
     """SVGP Matern52-ARD at configs[3]'s M = 2048, D = 32 on a minibatch of 16384: loss and every gradient of the
     unmodified reference; the M x M gradient of the raw Cholesky factor through its diagonal, 8 seeded projections
