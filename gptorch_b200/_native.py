@@ -409,6 +409,21 @@ def gemv_t(A, Y, out, beta=1.0):
     return out
 
 
+def rowdot(A, B, alpha=1.0, out=None, beta=0.0):
+    """out[i] = alpha * sum_j A[i][j] B[i][j] + beta * out[i] in one pass over A and B (no [rows x cols] temporary)."""
+    A, B = _c(A), _c(B)
+    if A.shape != B.shape:
+        raise ValueError("rowdot: shapes differ")
+    rows, cols = A.shape
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float64, device=A.device)
+        beta = 0.0
+    if rows:
+        call("gpb_rowdot", ptr(A), A.stride(0), ptr(B), B.stride(0), rows, cols, float(alpha), float(beta), ptr(out),
+             stream_ptr())
+    return out
+
+
 def gemm_splitk(mode, A, B, k_per_split, C3, beta=1.0, alpha=1.0, lower_only=False):
     """Split-K GEMM: slice s of the k range accumulates into C3[s] (C3: [splits, m, ld] with ld even)."""
     A = _gemm_operand(A)

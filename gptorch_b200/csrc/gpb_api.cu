@@ -22,6 +22,8 @@ int gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int 
            long ldo, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, int k, long ldv, double* out,
                  cudaStream_t stream);
+int rowdot(const double* A, long lda, const double* B, long ldb, long rows, int cols, double alpha, double beta,
+           double* out, cudaStream_t stream);
 int tri_zero_upper(double* A, int n, long lda, cudaStream_t stream);
 int add_diag(double* A, int n, long lda, const double* value, double host_value, cudaStream_t stream);
 int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
@@ -158,6 +160,10 @@ int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrow
   return logdet_sumsq(L, n, ldl, V, vrows, k, ldv, out, S(stream));
 }
 
+int gpb_rowdot(const double* A, long lda, const double* B, long ldb, long rows, int cols, double alpha, double beta,
+               double* out, void* stream) {
+  return rowdot(A, lda, B, ldb, rows, cols, alpha, beta, out, S(stream));
+}
 size_t gpb_gemv_t_workspace_bytes(long rows, int cols) { return gemv_t_workspace_bytes(rows, cols); }
 int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta,
                double* out, long ldo, void* workspace, size_t workspace_bytes, void* stream) {

@@ -367,6 +367,47 @@ int gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int 
   return GPB_OK;
 }
 
+// ================================================================================================
+// row-wise dot products: out[i] = sum_j A[i][j] B[i][j]  (variance epilogues of the sparse models)
+// ================================================================================================
+// One CTA per row, fixed-order reduction (deterministic).  HBM-bound: reads 16 * cols bytes per row once.
+__global__ void __launch_bounds__(256) rowdot_kernel(const double* __restrict__ A, long lda, const double* __restrict__ B,
+                                                     long ldb, int cols, double alpha, double beta,
+                                                     double* __restrict__ out) {
+  __shared__ double red[32];
+  const long i = blockIdx.x;
+  const double* a = A + i * lda;
+  const double* b = B + i * ldb;
+  double s = 0.0;
+  const bool vec = (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);
+  if (vec) {
+    const int c2 = cols >> 1;
+    for (int j = threadIdx.x; j < c2; j += blockDim.x) {
+      const double2 x = __ldcs(reinterpret_cast<const double2*>(a) + j);
+      const double2 y = __ldcs(reinterpret_cast<const double2*>(b) + j);
+      s = fma(x.x, y.x, s);
+      s = fma(x.y, y.y, s);
+    }
+    if ((cols & 1) && threadIdx.x == 0) s = fma(a[cols - 1], b[cols - 1], s);
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) s = fma(__ldcs(a + j), __ldcs(b + j), s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[i] = alpha * s + (beta != 0.0 ? beta * out[i] : 0.0);
+}
+
+int rowdot(const double* A, long lda, const double* B, long ldb, long rows, int cols, double alpha, double beta,
+           double* out, cudaStream_t stream) {
+  if (rows < 0 || cols < 0) return GPB_ERR_BADARG;
+  if (rows == 0) return GPB_OK;
+  if (!A || !B || !out || lda < cols || ldb < cols) return GPB_ERR_BADARG;
+  if (rows > 2147483647L) return GPB_ERR_UNSUPPORTED;
+  rowdot_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(A, lda, B, ldb, cols, alpha, beta, out);
+  count_launch();
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
 __global__ void tri_zero_upper_kernel(double* __restrict__ A, int n, long lda) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;

@@ -177,6 +177,11 @@ int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrow
 /* out[c][o] = beta * out[c][o] + sum_r A[r][c] * Y[r][o]:  A^T Y for a tall row panel A (rows x cols) and a few
  * right-hand sides (the "A @ err" statistic of gptorch/models/sparse_gpr.py:137 in row-panel layout).  HBM-bound:
  * A is read once; deterministic two-stage reduction. */
+/* out[i] = alpha * sum_j A[i][j] B[i][j] + beta * out[i] for i < rows: the row-wise reductions of the sparse models'
+ * predictive variance, sum(alpha ** 2, dim=1) / sum(gamma ** 2, dim=1) (gptorch/models/sparse_gpr.py:374-379,
+ * :186-190) and Kdiag - colsum(A * A) (gptorch/models/gpr.py:109-113), in one pass without an [rows x cols] temporary. */
+int gpb_rowdot(const double* A, long lda, const double* B, long ldb, long rows, int cols, double alpha, double beta,
+               double* out, void* stream);
 size_t gpb_gemv_t_workspace_bytes(long rows, int cols);
 int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta,
                double* out, long ldo, void* workspace, size_t workspace_bytes, void* stream);
