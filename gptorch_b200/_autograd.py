@@ -323,6 +323,117 @@ class CholeskyInverseFn(Function):
         return gL
 
 
+class TriInvTFn(Function):
+    """T = L^-T as a dense upper-triangular matrix, differentiable in L:  dL = -tril(T G^T T).  Used where the sparse
+    models apply L^-1 . L^-T to M x M quantities instead of solving against tall panels."""
+
+    @staticmethod
+    def forward(ctx, L, dinv):
+        T = _tinv(nv._gemm_operand(L.detach()), dinv)
+        ctx.save_for_backward(T)
+        return T
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        (T,) = ctx.saved_tensors
+        Gu = torch.triu(nv._c(G))                                       # T is upper triangular: only those entries count
+        M1 = nv.gemm(nv.GEMM_NT, T, Gu, flags=nv.GF_KLO_M | nv.GF_KLO_N)   # T G^T  (both upper: k >= row, k >= col)
+        gL = nv.gemm(nv.GEMM_NN, M1, T, alpha=-1.0, flags=nv.GF_KHI_N)    # (T G^T) T
+        gL.tril_()
+        return gL, None
+
+
+class SyrkFn(Function):
+    """U U^T (full symmetric result from the lower tiles); backward dU = (G + G^T) U.  `upper`: U is upper triangular
+    (U[i][k] = 0 for k < i), which halves the k-range."""
+
+    @staticmethod
+    def forward(ctx, U, upper=False):
+        ctx.upper = bool(upper)
+        ctx.save_for_backward(U)
+        flags = (nv.GF_KLO_M | nv.GF_KLO_N) if upper else 0
+        C = nv.gemm(nv.GEMM_NT, U, U, lower_only=True, flags=flags)
+        return torch.tril(C) + torch.tril(C, -1).t()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        (U,) = ctx.saved_tensors
+        S = nv._c(G + G.t())
+        gU = nv.gemm(nv.GEMM_NN, S, U)
+        if ctx.upper:
+            gU.triu_()
+        return gU, None
+
+
+class RowSumSqFn(Function):
+    """sum(A ** 2, dim=1) for a row panel in one pass (gpb_rowdot): the variance reductions of the predictive equations,
+    (A * A).sum(0) of gptorch/models/gpr.py:109-113 and sum(alpha ** 2, dim=1), sum(gamma ** 2, dim=1) of
+    gptorch/models/sparse_gpr.py:186-190, :374-379 (panels are row-major here), without the [rows x cols] temporary."""
+
+    @staticmethod
+    def forward(ctx, A):
+        A = nv._c(A)
+        ctx.save_for_backward(A)
+        return nv.rowdot(A, A)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (A,) = ctx.saved_tensors
+        return A * (2.0 * g)[:, None]
+
+
+SVGP_SPLITS = 4
+
+
+class SvgpMomentsFn(Function):
+    """(Kfu m, diag(Kfu C Kfu^T)) for a row panel Kfu [B, M], a symmetric C [M, M] and m [M, dy]: the q(f) moments of
+    SVGP._predict (gptorch/models/sparse_gpr.py:357-379) with the M x M algebra done first,
+        mean_i = k_i^T Kuu^-1 m_u,     var_i - Kdiag_i = k_i^T C k_i,   C = Kuu^-1 (S - Kuu) Kuu^-1,
+    i.e. ONE panel product Kfu C (2 B M^2 flop) instead of alpha = L^-1 Kuf, gamma = alpha beta and their adjoints
+    (6 B M^2 per loss+grad in the reference order, 3 B M^2 here).  backward: dKfu = 2 g_var . (Kfu C) + g_mean m^T (in
+    place on the saved product), dC = Kfu^T diag(g_var) Kfu (split-K Gram product), dm = Kfu^T g_mean."""
+
+    @staticmethod
+    def forward(ctx, Kfu, C, mvec):
+        Kfu, C, mvec = nv._c(Kfu), nv._gemm_operand(C), nv._c(mvec)
+        with nv.phase("svgp_panel_gemm"):
+            KC = nv.gemm(nv.GEMM_NN, Kfu, C)
+        with nv.phase("svgp_reduce"):
+            q = nv.rowdot(KC, Kfu)
+            mean = nv.gemv_n(Kfu, mvec)
+        ctx.save_for_backward(Kfu, KC, mvec)
+        return mean, q
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_mean, g_q):
+        Kfu, KC, mvec = ctx.saved_tensors
+        g_mean, g_q = nv._c(g_mean), nv._c(g_q).reshape(-1)
+        b, m = Kfu.shape
+        gC = gm = None
+        if ctx.needs_input_grad[1]:
+            with nv.phase("svgp_gram"):
+                Ks = Kfu * g_q[:, None]
+                ldm = m + (m & 1)
+                kper = max(16, ((b + SVGP_SPLITS - 1) // SVGP_SPLITS + 15) // 16 * 16)
+                C3 = torch.zeros((SVGP_SPLITS, m, ldm), dtype=torch.float64, device=Kfu.device)
+                nv.gemm_splitk(nv.GEMM_TN, Ks, Kfu, kper, C3, beta=0.0, lower_only=True)
+                del Ks
+                gC = C3.sum(0)[:, :m]
+                gC = torch.tril(gC) + torch.tril(gC, -1).t()
+        if ctx.needs_input_grad[2]:
+            gm = torch.zeros_like(mvec)
+            nv.gemv_t(Kfu, g_mean, gm, beta=0.0)
+        gK = None
+        if ctx.needs_input_grad[0]:
+            with nv.phase("svgp_reduce"):
+                gK = nv.rows_scale_add_outer_(KC, s=g_q, scale=2.0, G=g_mean, V=mvec)   # consumes the saved product
+        return gK, gC, gm
+
+
 class LogDetFn(Function):
     """sum(log(diag(L)))  (functions.lt_log_determinant, gptorch/functions.py:61-68)."""
 
@@ -379,7 +490,7 @@ class GemmFn(Function):
 # fused GPR log marginal likelihood
 # ------------------------------------------------------------------------------------------------------
 JITTER_TRIES = 10  # gptorch/functions.py:21
-VFE_PANEL_CACHE_BYTES = 8 << 30    # reference-order VFE: keep the solved A^T panels for backward up to this size
+VFE_PANEL_CACHE_BYTES = 16 << 30   # keep the streamed panels (Kfu, or A^T in the reference order) for backward up to this size
 VFE_SPLITS = 16    # k-slices of the streamed Gram products (fills the GPU when M x M has few tiles)
 
 
@@ -553,9 +664,10 @@ class VfeStatsFn(Function):
         ldm = m + (m & 1)
         AA3 = torch.zeros((VFE_SPLITS, m, ldm), dtype=torch.float64, device=X.device)
         AYf = torch.zeros((m, dy), dtype=torch.float64, device=X.device)
-        # Reference order only: keep the solved panels A^T for the backward pass when they fit a small budget
-        # (N*M*8 bytes); otherwise the backward pass rebuilds them (one more covariance build + solve per chunk).
-        keep = (not phi_form) and any(ctx.needs_input_grad) and n * ldm * 8 <= VFE_PANEL_CACHE_BYTES
+        # Keep the streamed panels for the backward pass when they fit a modest budget (N*M*8 bytes <= 16 GiB of the
+        # 180 GB); otherwise the backward pass rebuilds them chunk by chunk (one more covariance build, plus the solve in
+        # the reference order).
+        keep = any(ctx.needs_input_grad) and n * ldm * 8 <= VFE_PANEL_CACHE_BYTES
         cache = []
         for s in range(0, n, chunk):
             e = min(n, s + chunk)

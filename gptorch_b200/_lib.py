@@ -55,6 +55,9 @@ SIGNATURES = {
     "gpb_trsm_right_lt": (c_int, [c_void_p, c_int, c_long, c_void_p, c_void_p, c_int, c_long, c_void_p]),
     "gpb_logdet_sumsq": (c_int, [c_void_p, c_int, c_long, c_void_p, c_int, c_int, c_long, c_void_p, c_void_p]),
     "gpb_rowdot": (c_int, [c_void_p, c_long, c_void_p, c_long, c_long, c_int, c_double, c_double, c_void_p, c_void_p]),
+    "gpb_gemv_n": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_int, c_long, c_void_p, c_long, c_void_p]),
+    "gpb_rows_scale_add_outer": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_double, c_void_p, c_int, c_long,
+                                         c_void_p, c_long, c_void_p]),
     "gpb_gemv_t_workspace_bytes": (c_size_t, [c_long, c_int]),
     "gpb_gemv_t": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_int, c_long, c_double, c_void_p, c_long, c_void_p,
                            c_size_t, c_void_p]),

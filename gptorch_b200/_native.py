@@ -424,6 +424,29 @@ def rowdot(A, B, alpha=1.0, out=None, beta=0.0):
     return out
 
 
+def gemv_n(A, V):
+    """A @ V for a row panel A (rows x cols) and a few columns V (cols x dy); A is read once."""
+    A, V = _c(A), _c(V)
+    rows, cols = A.shape
+    out = torch.empty((rows, V.shape[1]), dtype=torch.float64, device=A.device)
+    if rows and V.shape[1]:
+        call("gpb_gemv_n", ptr(A), rows, cols, A.stride(0), ptr(V), V.shape[1], V.stride(0), ptr(out), out.stride(0),
+             stream_ptr())
+    return out
+
+
+def rows_scale_add_outer_(A, s=None, scale=1.0, G=None, V=None):
+    """In place: A[i][j] = scale * s[i] * A[i][j] + sum_o G[i][o] V[j][o]."""
+    rows, cols = A.shape
+    if G is not None:
+        G, V = _c(G), _c(V)
+    if rows:
+        call("gpb_rows_scale_add_outer", ptr(A), rows, cols, A.stride(0), ptr(_c(s).reshape(-1)) if s is not None else None,
+             float(scale), ptr(G), G.shape[1] if G is not None else 0, G.stride(0) if G is not None else 0, ptr(V),
+             V.stride(0) if V is not None else 0, stream_ptr())
+    return A
+
+
 def gemm_splitk(mode, A, B, k_per_split, C3, beta=1.0, alpha=1.0, lower_only=False):
     """Split-K GEMM: slice s of the k range accumulates into C3[s] (C3: [splits, m, ld] with ld even)."""
     A = _gemm_operand(A)

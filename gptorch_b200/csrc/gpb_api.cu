@@ -24,6 +24,10 @@ int logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrows, i
                  cudaStream_t stream);
 int rowdot(const double* A, long lda, const double* B, long ldb, long rows, int cols, double alpha, double beta,
            double* out, cudaStream_t stream);
+int gemv_n(const double* A, long rows, int cols, long lda, const double* V, int dy, long ldv, double* out, long ldo,
+           cudaStream_t stream);
+int rows_scale_add_outer(double* A, long rows, int cols, long lda, const double* s, double scale, const double* G, int dy,
+                         long ldg, const double* V, long ldv, cudaStream_t stream);
 int tri_zero_upper(double* A, int n, long lda, cudaStream_t stream);
 int add_diag(double* A, int n, long lda, const double* value, double host_value, cudaStream_t stream);
 int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
@@ -163,6 +167,14 @@ int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrow
 int gpb_rowdot(const double* A, long lda, const double* B, long ldb, long rows, int cols, double alpha, double beta,
                double* out, void* stream) {
   return rowdot(A, lda, B, ldb, rows, cols, alpha, beta, out, S(stream));
+}
+int gpb_gemv_n(const double* A, long rows, int cols, long lda, const double* V, int dy, long ldv, double* out, long ldo,
+               void* stream) {
+  return gemv_n(A, rows, cols, lda, V, dy, ldv, out, ldo, S(stream));
+}
+int gpb_rows_scale_add_outer(double* A, long rows, int cols, long lda, const double* s, double scale, const double* G,
+                             int dy, long ldg, const double* V, long ldv, void* stream) {
+  return rows_scale_add_outer(A, rows, cols, lda, s, scale, G, dy, ldg, V, ldv, S(stream));
 }
 size_t gpb_gemv_t_workspace_bytes(long rows, int cols) { return gemv_t_workspace_bytes(rows, cols); }
 int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta,

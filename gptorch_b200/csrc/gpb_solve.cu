@@ -408,6 +408,94 @@ int rowdot(const double* A, long lda, const double* B, long ldb, long rows, int 
   return GPB_OK;
 }
 
+// ================================================================================================
+// panel times a few vectors, and its adjoint update (mean / gradient epilogues of the sparse models)
+// ================================================================================================
+constexpr int GN_DY = 4;      // right-hand sides per pass
+constexpr int GN_ROWS = 4;    // rows per CTA (V is re-read from L1/L2 once per CTA)
+
+// out[i][o] = sum_j A[i][j] V[j][o]   (A: rows x cols panel, V: cols x dy, dy <= GN_DY per launch)
+__global__ void __launch_bounds__(256) gemv_n_kernel(const double* __restrict__ A, long rows, int cols, long lda,
+                                                     const double* __restrict__ V, int dy0, int dy, long ldv,
+                                                     double* __restrict__ out, long ldo) {
+  __shared__ double red[32];
+  const long r0 = static_cast<long>(blockIdx.x) * GN_ROWS;
+  double acc[GN_ROWS][GN_DY];
+#pragma unroll
+  for (int q = 0; q < GN_ROWS; ++q)
+#pragma unroll
+    for (int o = 0; o < GN_DY; ++o) acc[q][o] = 0.0;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    double v[GN_DY];
+#pragma unroll
+    for (int o = 0; o < GN_DY; ++o) v[o] = o < dy ? __ldg(V + static_cast<long>(j) * ldv + dy0 + o) : 0.0;
+#pragma unroll
+    for (int q = 0; q < GN_ROWS; ++q) {
+      if (r0 + q < rows) {
+        const double a = __ldcs(A + (r0 + q) * lda + j);
+#pragma unroll
+        for (int o = 0; o < GN_DY; ++o) acc[q][o] = fma(a, v[o], acc[q][o]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < GN_ROWS; ++q)
+#pragma unroll
+    for (int o = 0; o < GN_DY; ++o) {
+      if (o >= dy) break;                       // uniform
+      const double s = block_sum(acc[q][o], red);
+      if (threadIdx.x == 0 && r0 + q < rows) out[(r0 + q) * ldo + dy0 + o] = s;
+    }
+}
+
+int gemv_n(const double* A, long rows, int cols, long lda, const double* V, int dy, long ldv, double* out, long ldo,
+           cudaStream_t stream) {
+  if (rows < 0 || cols <= 0 || dy <= 0) return GPB_ERR_BADARG;
+  if (rows == 0) return GPB_OK;
+  if (!A || !V || !out || lda < cols || ldv < dy || ldo < dy) return GPB_ERR_BADARG;
+  const long ctas = (rows + GN_ROWS - 1) / GN_ROWS;
+  if (ctas > 2147483647L) return GPB_ERR_UNSUPPORTED;
+  for (int dy0 = 0; dy0 < dy; dy0 += GN_DY) {
+    gemv_n_kernel<<<static_cast<unsigned>(ctas), 256, 0, stream>>>(A, rows, cols, lda, V, dy0, std::min(GN_DY, dy - dy0), ldv,
+                                                                  out, ldo);
+    count_launch();
+    GPB_CUDA_CHECK(cudaGetLastError());
+  }
+  return GPB_OK;
+}
+
+// A[i][j] <- scale * s[i] * A[i][j] + sum_o G[i][o] V[j][o]   (s may be NULL = 1; G / V may be NULL = no outer product)
+__global__ void __launch_bounds__(256) rows_scale_add_outer_kernel(double* __restrict__ A, long rows, int cols, long lda,
+                                                                   const double* __restrict__ s, double scale,
+                                                                   const double* __restrict__ G, int dy, long ldg,
+                                                                   const double* __restrict__ V, long ldv) {
+  const long i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  double v = scale * (s ? s[i] : 1.0) * A[i * lda + j];
+  if (G) {
+    for (int o = 0; o < dy; ++o) v = fma(G[i * ldg + o], __ldg(V + static_cast<long>(j) * ldv + o), v);
+  }
+  A[i * lda + j] = v;
+}
+
+int rows_scale_add_outer(double* A, long rows, int cols, long lda, const double* s, double scale, const double* G, int dy,
+                         long ldg, const double* V, long ldv, cudaStream_t stream) {
+  if (rows < 0 || cols <= 0) return GPB_ERR_BADARG;
+  if (rows == 0) return GPB_OK;
+  if (!A || lda < cols || (G && (!V || dy <= 0 || ldg < dy || ldv < dy))) return GPB_ERR_BADARG;
+  const long per = 65535;                       // gridDim.y limit
+  for (long r0 = 0; r0 < rows; r0 += per) {
+    const long nr = std::min(per, rows - r0);
+    dim3 grid((cols + 255) / 256, static_cast<unsigned>(nr));
+    rows_scale_add_outer_kernel<<<grid, 256, 0, stream>>>(A + r0 * lda, nr, cols, lda, s ? s + r0 : nullptr, scale,
+                                                         G ? G + r0 * ldg : nullptr, dy, ldg, V, ldv);
+    count_launch();
+    GPB_CUDA_CHECK(cudaGetLastError());
+  }
+  return GPB_OK;
+}
+
 __global__ void tri_zero_upper_kernel(double* __restrict__ A, int n, long lda) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;

@@ -88,7 +88,7 @@ class GPR(GPModel):
         At = trtrs(k_sy.t(), L).t()                          # (L^-1 k_ys)^T, solved on the row panel k_sy L^-T
         mean_f = mm(At, V) + self.mean_function(x_new)
         if diag:
-            var_f = (self.kernel.Kdiag(x_new) - (At * At).sum(1))[:, None].expand_as(mean_f)
+            var_f = (self.kernel.Kdiag(x_new) - ag.RowSumSqFn.apply(At))[:, None].expand_as(mean_f)   # fused Kdiag - colsum(A^2)
         else:
             var_f = self.kernel.K(x_new) - mm_nt(At, At)
         return mean_f, var_f

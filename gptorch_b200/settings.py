@@ -42,3 +42,8 @@ graph_max_rows = 4096      # larger evaluations are compute-bound (and use the l
 # magnitude inside the 1e-7 tolerance.  False = always the reference's order of operations; True = always the Phi form.
 vfe_phi_form = "auto"
 vfe_phi_cond_max = 2.0e5
+
+# SVGP data term (SvgpMomentsFn): "auto" forms C = Kuu^-1 (S - Kuu) Kuu^-1 first and evaluates the batch moments with one
+# panel product (3 B M^2 flop per loss+grad instead of 6 B M^2) under the same conditioning gate as the VFE Phi form, for
+# batches of at least 16 M rows with the Gaussian likelihood.  False = the reference's order; True = always.
+svgp_quadratic_form = "auto"

@@ -182,6 +182,14 @@ int gpb_logdet_sumsq(const double* L, int n, long ldl, const double* V, int vrow
  * :186-190) and Kdiag - colsum(A * A) (gptorch/models/gpr.py:109-113), in one pass without an [rows x cols] temporary. */
 int gpb_rowdot(const double* A, long lda, const double* B, long ldb, long rows, int cols, double alpha, double beta,
                double* out, void* stream);
+/* out[i][o] = sum_j A[i][j] V[j][o]: a row panel times a few vectors (the predictive mean alpha @ t of
+ * gptorch/models/sparse_gpr.py:369, K(x*, X) @ a of gptorch/models/gpr.py:107) -- A is read once. */
+int gpb_gemv_n(const double* A, long rows, int cols, long lda, const double* V, int dy, long ldv, double* out, long ldo,
+               void* stream);
+/* In place: A[i][j] = scale * s[i] * A[i][j] + sum_o G[i][o] V[j][o]  (s == NULL: 1; G == NULL: no outer product).  The
+ * adjoint of the two reductions above in one pass: d/dA of sum_i s_i (row quadratic form) plus (A V) against G. */
+int gpb_rows_scale_add_outer(double* A, long rows, int cols, long lda, const double* s, double scale, const double* G,
+                             int dy, long ldg, const double* V, long ldv, void* stream);
 size_t gpb_gemv_t_workspace_bytes(long rows, int cols);
 int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta,
                double* out, long ldo, void* workspace, size_t workspace_bytes, void* stream);

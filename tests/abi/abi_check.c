@@ -29,7 +29,8 @@ int main(int argc, char** argv) {
       "gpb_kern_bwd_workspace_bytes", "gpb_kern_bwd", "gpb_kern_bwd_mul", "gpb_kern_sop_fwd", "gpb_linear_kdiag",
       "gpb_potrf_lower", "gpb_tri_diag_inverse", "gpb_potri_workspace_bytes", "gpb_potri_lower", "gpb_trtri_upper",
       "gpb_potri_assemble", "gpb_tri_zero_upper", "gpb_add_diag", "gpb_trsv_workspace_bytes", "gpb_trsv_lower",
-      "gpb_trsm_right_lt", "gpb_logdet_sumsq", "gpb_rowdot", "gpb_gemv_t_workspace_bytes", "gpb_gemv_t", "gpb_gemm", "gpb_gemm_splitk",
+      "gpb_trsm_right_lt", "gpb_logdet_sumsq", "gpb_rowdot", "gpb_gemv_n",
+      "gpb_rows_scale_add_outer", "gpb_gemv_t_workspace_bytes", "gpb_gemv_t", "gpb_gemm", "gpb_gemm_splitk",
       "gpb_gpr_grad_workspace_bytes", "gpb_gpr_grad"};
   void* lib;
   size_t i;

@@ -402,6 +402,57 @@ def test_svgp_named_size_pin_m2048_b16384():
     assert abs(np.linalg.norm(G) - c.get(nm, "g_q_sqrt_raw_fro").item()) <= GRAD_TOL * c.get(nm, "g_q_sqrt_raw_fro").item()
 
 
+@pytest.mark.parametrize("name", _SVGP.names + ["svgp_m2048_b16384"])
+def test_svgp_quadratic_form_meets_the_parity_tolerances(name):
+    """settings.svgp_quadratic_form = True (C = Kuu^-1 (S - Kuu) Kuu^-1 first, one panel product; 3 B M^2 flop instead of
+    the reference order's 6 B M^2): loss <= 1e-9 and every gradient <= 1e-7 against the unmodified reference on every
+    SVGP golden, including the M = 2048 / D = 32 pin."""
+    from conftest import Cases
+    from oracle import gp_oracle as O
+    from gptorch_b200 import likelihoods, kernels, settings
+    from gptorch_b200.models import SVGP
+    large = name.startswith("svgp_m2048")
+    np.random.seed(0)
+    if large:
+        c = Cases("large_cases.npz")
+        n, d, m, batch = 65536, 32, 2048, 16384
+        X, Y, g = O.synth_regression(n, d)
+        Z = O.synth_inducing(X, m, g)
+        idx = torch.randperm(n, generator=g)[:batch]
+        model = SVGP(X.numpy(), Y.numpy(), kernels.Matern52(d, ARD=True), inducing_points=Z.numpy(),
+                     likelihood=likelihoods.Gaussian(variance=0.01), batch_size=batch)
+        q_mu, raw = O.seeded_q(m, 1)
+        xb, yb = X[idx].cuda(), Y[idx].cuda()
+    else:
+        c = _SVGP
+        kind, d = str(c.get(name, "kind")), int(c.get(name, "d"))
+        model = SVGP(c.get(name, "X"), c.get(name, "Y"), _kernel(kind, d, c.get(name, "ell"), c.get(name, "variance")),
+                     inducing_points=c.get(name, "Z"), likelihood=likelihoods.Gaussian(variance=float(c.get(name, "noise"))))
+        q_mu, raw = torch.as_tensor(c.get(name, "q_mu")), torch.as_tensor(c.get(name, "q_sqrt_raw"))
+        xb, yb = torch.as_tensor(c.get(name, "xb")).cuda(), torch.as_tensor(c.get(name, "yb")).cuda()
+    model.induced_output_mean.data.copy_(q_mu)
+    model.induced_output_chol_cov.data.copy_(raw)
+    settings.svgp_quadratic_form = True
+    try:
+        loss = model.loss(xb, yb)
+        loss.backward()
+    finally:
+        settings.svgp_quadratic_form = "auto"
+    gr = _grads(model)
+    assert rel_err(loss.item(), c.get(name, "loss")) <= LML_TOL
+    assert rel_err(gr["kernel.variance"], c.get(name, "g_variance")) <= GRAD_TOL
+    assert rel_err(gr["kernel.length_scales"], c.get(name, "g_length_scales")) <= GRAD_TOL
+    assert rel_err(gr["likelihood.variance"], c.get(name, "g_noise")) <= GRAD_TOL
+    assert rel_err(gr["Z"], c.get(name, "g_Z")) <= GRAD_TOL
+    assert rel_err(gr["induced_output_mean"], c.get(name, "g_q_mu")) <= GRAD_TOL
+    G = gr["induced_output_chol_cov"]
+    if large:
+        assert rel_err(np.diag(G), c.get(name, "g_q_sqrt_raw_diag")) <= GRAD_TOL
+        assert rel_err(O.projections(G), c.get(name, "g_q_sqrt_raw_proj")) <= GRAD_TOL
+    else:
+        assert rel_err(G, c.get(name, "g_q_sqrt_raw")) <= GRAD_TOL
+
+
 def test_svgp_bound_with_a_custom_likelihood_uses_propagate_log():
     """Only the package's Gaussian has expected_log_density; any other Likelihood subclass goes through the abstract
     propagate_log(Normal(mean, sqrt(var)), y) exactly as the reference calls it (gptorch/models/sparse_gpr.py:274-281)."""

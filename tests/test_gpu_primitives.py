@@ -260,3 +260,47 @@ def test_full_size_identities_n32768():
         lm = model.loss().item()
     fd = (lp - lm) / (2 * eps)
     assert abs(fd - analytic) <= 1e-5 * abs(analytic)
+
+
+def test_row_reductions_and_panel_vector_products():
+    """gpb_rowdot / gpb_gemv_n / gpb_rows_scale_add_outer (the variance and mean epilogues of the predictive equations)
+    on ragged, padded and unaligned panels against torch."""
+    from gptorch_b200 import _native as nv, _autograd as ag
+    g = torch.Generator().manual_seed(9)
+    for rows, cols, dy in ((1, 1, 1), (37, 129, 3), (300, 1000, 1), (513, 77, 6)):
+        A = torch.randn(rows, cols, generator=g, dtype=torch.float64).cuda()
+        B = torch.randn(rows, cols, generator=g, dtype=torch.float64).cuda()
+        V = torch.randn(cols, dy, generator=g, dtype=torch.float64).cuda()
+        G = torch.randn(rows, dy, generator=g, dtype=torch.float64).cuda()
+        s = torch.randn(rows, generator=g, dtype=torch.float64).cuda()
+        assert rel_err(nv.rowdot(A, B).cpu().numpy(), (A * B).sum(1).cpu().numpy()) < 1e-13
+        pad = torch.zeros(rows, cols + 3, dtype=torch.float64, device="cuda")
+        pad[:, 1:cols + 1] = A                                   # unaligned base, padded rows
+        assert rel_err(nv.rowdot(pad[:, 1:cols + 1], B).cpu().numpy(), (A * B).sum(1).cpu().numpy()) < 1e-13
+        assert rel_err(nv.gemv_n(A, V).cpu().numpy(), (A @ V).cpu().numpy()) < 1e-13
+        ref = 2.0 * s[:, None] * A + G @ V.t()
+        out = nv.rows_scale_add_outer_(A.clone(), s=s, scale=2.0, G=G, V=V)
+        assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 1e-13
+        Ac = A.clone().requires_grad_(True)
+        (ag.RowSumSqFn.apply(Ac) * s).sum().backward()
+        assert rel_err(Ac.grad.cpu().numpy(), (2.0 * s[:, None] * A).cpu().numpy()) < 1e-13
+
+
+def test_triangular_inverse_and_syrk_nodes_match_autograd():
+    """TriInvTFn (T = L^-T) and SyrkFn (U U^T), the M x M building blocks of the sparse models' quadratic forms."""
+    from gptorch_b200 import _autograd as ag, _native as nv
+    n = 300
+    K = _spd(n)
+    Lref = torch.linalg.cholesky(K)
+    g = torch.Generator().manual_seed(3)
+    W = torch.randn(n, n, generator=g, dtype=torch.float64)
+    Lc = Lref.cuda().requires_grad_(True)
+    T = ag.TriInvTFn.apply(Lc, nv.tri_diag_inverse(nv._c(Lc.detach())))
+    C = ag.SyrkFn.apply(T, True)
+    ((T * W.cuda()).sum() + (C * W.cuda()).sum()).backward()
+    Lr = Lref.clone().requires_grad_(True)
+    Tr = torch.linalg.solve_triangular(Lr, torch.eye(n, dtype=torch.float64), upper=False).t()
+    ((Tr * W).sum() + ((Tr @ Tr.t()) * W).sum()).backward()
+    assert rel_err(T.detach().cpu().numpy(), Tr.detach().numpy()) < 1e-10
+    assert rel_err(C.detach().cpu().numpy(), (Tr @ Tr.t()).detach().numpy()) < 1e-10
+    assert rel_err(torch.tril(Lc.grad).cpu().numpy(), torch.tril(Lr.grad).numpy()) < 1e-8
