@@ -100,10 +100,17 @@ def bench_vfe(rank, world, device, steps=3):
     grads = torch.cat([model.kernel.length_scales.grad.reshape(-1), model.kernel.variance.grad.reshape(-1),
                        model.likelihood.variance.grad.reshape(-1), model.Z.grad.reshape(-1)]).clone()
     flop = 3.0 * VFE_N * VFE_M ** 2 + 6.0 * VFE_N * VFE_M * VFE_D            # SURVEY 8d algorithmic count
+    cond = getattr(model, "last_kuu_condition", None)
+    from gptorch_b200 import settings
+    phi = cond is not None and cond <= settings.vfe_phi_cond_max
     out = {"workload": "VFE Rbf-ARD fp64 N=%d D=%d M=%d loss+grad (configs[2]), rows sharded over %d rank(s)"
                        % (VFE_N, VFE_D, VFE_M, world),
            "scaling": "strong", "ms_per_eval": ms, "evals_per_s": 1000.0 / ms, "rows_per_s": VFE_N / (ms / 1000.0),
            "loss": float(loss.item()),
+           "form": ("Phi form, 3 N M^2 + 6 N M D flop executed (condition-gated: estimated cond_2(Kuu) = %.3g <= %.3g)"
+                    % (cond, settings.vfe_phi_cond_max)) if phi else
+                   "reference order of operations, 5 N M^2 flop executed (estimated cond_2(Kuu) = %s)" % cond,
+           "flop_counted": "3 N M^2 + 6 N M D (SURVEY 8d algorithmic count)",
            "algorithmic_tflops_per_gpu": flop / world / (ms / 1000.0) / 1e12,
            "frac_of_fp64_peak": flop / world / (ms / 1000.0) / 1e12 / FP64_PEAK_TFLOPS,
            "collectives": "all_reduce(M*M + M*dy + 2 doubles) forward, all_reduce(D + 1 + M*D doubles) backward",
@@ -159,7 +166,12 @@ def bench_svgp(rank, world, device, steps=3):
     _step(model, post)
     ms, loss = _timed(lambda: _step(model, post), steps, world, device)
     nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
-    flop = 1.7e12                                                            # ~1.7e12 flop per step and GPU
+    from gptorch_b200 import settings
+    cond = getattr(model, "last_kuu_condition", None)
+    quad = cond is not None and cond <= settings.vfe_phi_cond_max
+    # flop actually executed per step and GPU: the quadratic form needs 3 B M^2 (one panel product 2 B M^2, one Gram
+    # product B M^2) + 4 B M D, the reference order 6 B M^2 (SURVEY 8d's ~1.7e12); both + O(M^3) replicated algebra
+    flop = (3.0 if quad else 6.0) * SVGP_B * SVGP_M ** 2 + 4.0 * SVGP_B * SVGP_M * SVGP_D + 20.0 * SVGP_M ** 3
     # replicas must stay identical: same parameters in, all-reduced gradients out
     chk = model.induced_output_mean.grad.abs().sum().reshape(1).clone()
     lo, hi = chk.clone(), chk.clone()
@@ -170,6 +182,10 @@ def bench_svgp(rank, world, device, steps=3):
                        "shard of %d rows is resident in HBM)" % (SVGP_M, SVGP_D, SVGP_B, world, SVGP_ROWS),
            "scaling": "weak", "ms_per_step": ms, "points_per_s": world * SVGP_B / (ms / 1000.0),
            "loss_rank0": float(loss.item()),
+           "form": ("quadratic form (M x M algebra first), 3 B M^2 flop executed (condition-gated: estimated cond_2(Kuu) = "
+                    "%.3g <= %.3g)" % (cond, settings.vfe_phi_cond_max)) if quad else
+                   "reference order of operations, 6 B M^2 flop executed (estimated cond_2(Kuu) = %s)" % cond,
+           "flop_counted": "executed: %.3g per step and GPU" % flop,
            "algorithmic_tflops_per_gpu": flop / (ms / 1000.0) / 1e12,
            "frac_of_fp64_peak": flop / (ms / 1000.0) / 1e12 / FP64_PEAK_TFLOPS,
            "collectives": "all_reduce(flat gradient, %d doubles = %.1f MB) per step" % (nparam, nparam * 8 / 1e6),

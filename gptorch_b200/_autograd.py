@@ -619,11 +619,13 @@ def kuu_condition_estimate(L, T, iters=8):
     m = L.shape[0]
     Lt, Tt = L.t().contiguous(), T.t().contiguous()
     out = []
-    for A, At in ((L, Lt), (T, Tt)):                 # v <- A (A^T v)
+    # Kuu is entrywise positive for the stationary families: its dominant (Perron) eigenvector is close to the start
+    # vector and half the iterations suffice; the small end of the spectrum (T T^T) gets the full count
+    for A, At, its in ((L, Lt, max(2, iters // 2)), (T, Tt, iters)):                 # v <- A (A^T v)
         v = torch.full((m, 1), 1.0 / math.sqrt(m), dtype=torch.float64, device=L.device)
         u = torch.empty_like(v)
         lam = None
-        for _ in range(iters):
+        for _ in range(its):
             nv.gemv_t(A, v, u, beta=0.0)            # u = A^T v
             nv.gemv_t(At, u, v, beta=0.0)           # v = A u
             lam = torch.linalg.vector_norm(v)

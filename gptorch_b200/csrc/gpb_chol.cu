@@ -16,6 +16,9 @@
 //               to the strictly-lower blocks; diagonal blocks go to a side buffer because the diagonal
 //               blocks of T are still being read by other CTAs.
 #include "gpb_gemm.cuh"
+#include <vector>
+#include <cstdlib>
+#include <algorithm>
 #include <algorithm>
 
 namespace gpb {
@@ -393,24 +396,56 @@ static int syrk_update(CholCtx& c, int r0, int m, int k0, int k) {
   return gemm_launch(GEMM_NT, c.mapA128, c.mapA128, g, c.stream);
 }
 
+// Panel schedule: widths (multiples of the 128 block) of the look-ahead panels; the last entry is the tail, which is
+// factored by the plain recursion once the trailing matrix is too small for a bulk update to hide the panel chain.
+// GPB_LA_PANEL / GPB_LA_FIRST / GPB_LA_TAIL override the defaults (tuning aid; read once).
+static int env_int(const char* name, int fallback) {
+  const char* v = getenv(name);
+  if (!v || !*v) return fallback;
+  const int x = atoi(v);
+  return x > 0 ? (x + NB - 1) / NB * NB : fallback;
+}
+
+static void panel_schedule(int n, std::vector<int>& starts) {
+  static const int w = env_int("GPB_LA_PANEL", LA_PANEL);
+  static const int first = env_int("GPB_LA_FIRST", LA_PANEL);
+  static const int tail = env_int("GPB_LA_TAIL", LA_PANEL);
+  starts.clear();
+  int c = 0;
+  starts.push_back(0);
+  c = std::min(first, n);
+  while (n - c > tail) {
+    starts.push_back(c);
+    c += w;
+  }
+  if (c < n) starts.push_back(c);
+  starts.push_back(n);
+}
+
 static int potrf_lookahead(CholCtx& c) {
   AuxStream* aux = nullptr;
   int rc = get_aux(&aux);
   if (rc) return rc;
   const cudaStream_t s0 = c.stream, s1 = aux->stream;
-  const int n = c.n, w = LA_PANEL;
+  const int n = c.n;
+  std::vector<int> st;
+  panel_schedule(n, st);
+  const int np = static_cast<int>(st.size()) - 1;     // panels [st[p], st[p+1])
   GPB_CUDA_CHECK(cudaEventRecord(aux->ev_fork, s0));
   GPB_CUDA_CHECK(cudaStreamWaitEvent(s1, aux->ev_fork, 0));
   // panel 0
   c.stream = s1;
-  rc = potrf_rec(c, 0, w);
+  rc = potrf_rec(c, 0, st[1]);
   if (rc) return rc;
-  rc = trsm_right_rec(c, w, n - w, 0, w);
-  if (rc) return rc;
+  if (st[1] < n) {
+    rc = trsm_right_rec(c, st[1], n - st[1], 0, st[1]);
+    if (rc) return rc;
+  }
   GPB_CUDA_CHECK(cudaEventRecord(aux->ev_panel, s1));
-  for (int c0 = 0; c0 + w < n; c0 += w) {
-    const int c1 = c0 + w;
-    const int w1 = std::min(w, n - c1);
+  for (int p = 0; p + 1 < np; ++p) {
+    const int c0 = st[p], w = st[p + 1] - st[p];
+    const int c1 = st[p + 1];
+    const int w1 = st[p + 2] - c1;
     const int c2 = c1 + w1;
     GPB_CUDA_CHECK(cudaStreamWaitEvent(s0, aux->ev_panel, 0));
     // 3a: bring the columns of the next panel up to date
