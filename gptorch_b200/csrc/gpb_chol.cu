@@ -17,6 +17,9 @@
 //               blocks of T are still being read by other CTAs.
 #include "gpb_gemm.cuh"
 #include <vector>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <cstdlib>
 #include <algorithm>
 #include <algorithm>
@@ -266,7 +269,7 @@ diag_block_kernel(double* __restrict__ A0, long lda, int n, double* __restrict__
 
 static int launch_diag_blocks(double* A0, long lda, int n, double* dinv, int* info, int j_first, int nblocks,
                               int do_factor, cudaStream_t stream) {
-  static int smem_state[GPB_MAX_DEVICES] = {0};
+  static std::atomic<int> smem_state[GPB_MAX_DEVICES];
   if (int rc = ensure_dynamic_smem(diag_block_kernel, DG_SMEM_BYTES, smem_state)) return rc;
   diag_block_kernel<<<nblocks, DG_THREADS, DG_SMEM_BYTES, stream>>>(A0, lda, n, dinv, info, j_first, do_factor);
   count_launch();
@@ -356,7 +359,7 @@ static inline long npad128(long n) { return (n + NB - 1) / NB * NB; }
 //
 // 3b(p) only reads panel p and writes columns right of panel p+1, S1 only touches the columns of panel p+1.
 constexpr int LA_PANEL = 2048;
-constexpr int LA_MIN_N = 3 * LA_PANEL;
+constexpr int LA_MIN_N = 3072;
 
 struct AuxStream {
   cudaStream_t stream = nullptr;
@@ -364,12 +367,15 @@ struct AuxStream {
   int device = -1;
 };
 
-static int get_aux(AuxStream** out) {
-  static AuxStream aux[64];
+// One side stream + event set per (device, caller stream): two factorisations issued on different caller streams of the
+// same device never share events, and the table itself is guarded (the library may be called from several host threads).
+static int get_aux(cudaStream_t caller, AuxStream** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, AuxStream> table;
   int dev = 0;
   GPB_CUDA_CHECK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return GPB_ERR_UNSUPPORTED;
-  AuxStream& a = aux[dev];
+  std::lock_guard<std::mutex> lock(mu);
+  AuxStream& a = table[std::make_pair(dev, caller)];
   if (a.stream == nullptr) {
     int lo = 0, hi = 0;
     GPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -407,9 +413,13 @@ static int env_int(const char* name, int fallback) {
 }
 
 static void panel_schedule(int n, std::vector<int>& starts) {
-  static const int w = env_int("GPB_LA_PANEL", LA_PANEL);
-  static const int first = env_int("GPB_LA_FIRST", LA_PANEL);
-  static const int tail = env_int("GPB_LA_TAIL", LA_PANEL);
+  // measured on B200 (tools/bench_potrf.py sweeps, profiles/r02_potrf_panel_sweep.txt): narrow panels win while the
+  // trailing updates are short (n = 8192: 512 columns 10.7 ms vs 2048 columns 12.7 ms vs plain recursion 13.4 ms), wide
+  // panels once the k-length of the trailing GEMMs dominates (n = 32768: 2048 columns 354 ms, 1024 columns 357 ms)
+  const int def = n <= 16384 ? 512 : (n <= 24576 ? 1024 : LA_PANEL);
+  static const int w_env = env_int("GPB_LA_PANEL", 0), first_env = env_int("GPB_LA_FIRST", 0),
+                   tail_env = env_int("GPB_LA_TAIL", 0);
+  const int w = w_env ? w_env : def, first = first_env ? first_env : w, tail = tail_env ? tail_env : w;
   starts.clear();
   int c = 0;
   starts.push_back(0);
@@ -424,7 +434,7 @@ static void panel_schedule(int n, std::vector<int>& starts) {
 
 static int potrf_lookahead(CholCtx& c) {
   AuxStream* aux = nullptr;
-  int rc = get_aux(&aux);
+  int rc = get_aux(c.stream, &aux);
   if (rc) return rc;
   const cudaStream_t s0 = c.stream, s1 = aux->stream;
   const int n = c.n;
@@ -495,7 +505,8 @@ int potrf_lower(double* A, int n, long lda, double* dinv, int* info, cudaStream_
   if (rc) return rc;
   rc = make_tmap_f64(&c.mapD128, dinv, npad128(n), NB, NB, 32);
   if (rc) return rc;
-  if (n >= LA_MIN_N) return potrf_lookahead(c);
+  static const int la_min = env_int("GPB_LA_MIN_N", LA_MIN_N);
+  if (n >= la_min) return potrf_lookahead(c);
   return potrf_rec(c, 0, n);
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <atomic>
 
 #define GPB_OK 0
 #define GPB_ERR_BADARG (-1)
@@ -32,14 +33,15 @@ void reset_launch_count();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember the largest size set for each device.
 // `state` is a per-kernel static array of GPB_MAX_DEVICES ints, zero-initialised.
 constexpr int GPB_MAX_DEVICES = 64;
+// (atomics: the library may be entered from several host threads; setting the attribute twice is harmless.)
 template <typename KernelT>
-inline int ensure_dynamic_smem(KernelT kernel, int bytes, int* state) {
+inline int ensure_dynamic_smem(KernelT kernel, int bytes, std::atomic<int>* state) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= GPB_MAX_DEVICES) return GPB_ERR_CUDA;
-  if (bytes > state[dev]) {
+  if (bytes > state[dev].load(std::memory_order_relaxed)) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) { set_last_error(e, __FILE__, __LINE__); return GPB_ERR_CUDA; }
-    state[dev] = bytes;
+    state[dev].store(bytes, std::memory_order_relaxed);
   }
   return GPB_OK;
 }

@@ -384,7 +384,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 template <int MODE, class Cfg>
 static int launch_cfg(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmKParams kp, const GemmArgs& a,
                       cudaStream_t stream) {
-  static int smem_state[GPB_MAX_DEVICES] = {0};
+  static std::atomic<int> smem_state[GPB_MAX_DEVICES];
   if (int rc = ensure_dynamic_smem(gemm_dmma_kernel<MODE, Cfg>, Cfg::SMEM_BYTES, smem_state)) return rc;
   kp.tiles_m = (a.M + Cfg::BM - 1) / Cfg::BM;
   kp.tiles_n = (a.N + Cfg::BN - 1) / Cfg::BN;

@@ -863,7 +863,7 @@ size_t kern_bwd_workspace_bytes(int n1, int n2, int D) {
 
 template <bool GPR, int DC, bool G2, int KIND>
 static int kbwd_launch_kind(const KbwdParams& p, int ncb, size_t smem, cudaStream_t stream) {
-  static int smem_state[GPB_MAX_DEVICES] = {0};
+  static std::atomic<int> smem_state[GPB_MAX_DEVICES];
   if (int rc = ensure_dynamic_smem(kern_bwd_kernel<GPR, DC, G2, KIND>, static_cast<int>(smem), smem_state)) return rc;
   dim3 grid(ncb, p.strips);
   kern_bwd_kernel<GPR, DC, G2, KIND><<<grid, KB_THREADS, smem, stream>>>(p);
@@ -887,7 +887,7 @@ static int kbwd_launch_cfg(const KbwdParams& p, int ncb, size_t smem, cudaStream
 // ---- DMMA path: dispatch over (family, padded D, GPR / dense, with / without the column gradient) -----------------------
 template <int KIND, int DP, bool GPR, bool G2>
 static int kbwd_mma_launch_one(const KbwdParams& p, int ncb, cudaStream_t stream) {
-  static int smem_state[GPB_MAX_DEVICES] = {0};
+  static std::atomic<int> smem_state[GPB_MAX_DEVICES];
   const size_t smem = kbwd_mma_smem_bytes<DP, GPR>();
   if (int rc = ensure_dynamic_smem(kern_bwd_mma_kernel<KIND, DP, GPR, G2>, static_cast<int>(smem), smem_state)) return rc;
   dim3 grid(ncb, p.strips);
