@@ -83,10 +83,12 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
   for (int d0 = 0; d0 < p.D; d0 += KF_DC) {
     __syncthreads();
     if (tid < KF_DC) {
+      // per-dimension factor: the variance v_d for Linear, 1 / ell_d otherwise -- ONE division per dimension and CTA; the
+      // staging loop below multiplies (a division per staged element was a quarter of this kernel's instructions)
       const int d = d0 + tid;
       double s = 1.0;
       if (d < p.D) s = p.ell[p.ell_len == 1 ? 0 : d];
-      scale[tid] = s;
+      scale[tid] = linear ? s : 1.0 / s;
     }
     __syncthreads();
     for (int idx = tid; idx < (KF_TM + KF_TN) * KF_DC; idx += KF_THREADS) {
@@ -96,14 +98,14 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
       if (row < KF_TM) {
         if (d < p.D && m0 + row < p.n1) {
           const double x = p.X[static_cast<long>(m0 + row) * p.ldx + d];
-          v = linear ? x * scale[k] : x / scale[k];
+          v = x * scale[k];
         }
         As[row * KF_LD + k] = v;
       } else {
         const int rb = row - KF_TM;
         if (d < p.D && n0 + rb < p.n2) {
           const double x = p.X2[static_cast<long>(n0 + rb) * p.ldx2 + d];
-          v = linear ? x : x / scale[k];
+          v = linear ? x : x * scale[k];
         }
         Bs[rb * KF_LD + k] = v;
       }
@@ -521,12 +523,12 @@ __global__ void __launch_bounds__(BM_THREADS, (DP <= 16 ? 2 : 1)) kern_bwd_mma_k
   const int D = p.D;
   const int dy = GPR ? p.dy : 0;
 
-  if (t < DP) ellv[t] = t < D ? p.ell[p.ell_len == 1 ? 0 : t] : 1.0;
+  if (t < DP) ellv[t] = t < D ? 1.0 / p.ell[p.ell_len == 1 ? 0 : t] : 1.0;     // reciprocal length scales
   __syncthreads();
   for (int idx = t; idx < 128 * DP; idx += BM_THREADS) {
     const int cc = idx / DP, d = idx - cc * DP;
     double v = 0.0;
-    if (d < D && c0 + cc < p.n2) v = p.X2[static_cast<long>(c0 + cc) * p.ldx2 + d] / ellv[d];
+    if (d < D && c0 + cc < p.n2) v = p.X2[static_cast<long>(c0 + cc) * p.ldx2 + d] * ellv[d];
     X2a[cc * LDA + d] = v;
     if (SPLIT) X2b[cc * LDB + d] = v;
   }
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(BM_THREADS, (DP <= 16 ? 2 : 1)) kern_bwd_mma_k
     for (int idx = t; idx < 64 * DP; idx += BM_THREADS) {
       const int rr = idx / DP, d = idx - rr * DP;
       double v = 0.0;
-      if (d < D && m0 + rr < p.n1) v = p.X1[static_cast<long>(m0 + rr) * p.ldx1 + d] / ellv[d];
+      if (d < D && m0 + rr < p.n1) v = p.X1[static_cast<long>(m0 + rr) * p.ldx1 + d] * ellv[d];
       X1s[rr * LDA + d] = v;
     }
     if (GPR) {
