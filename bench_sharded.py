@@ -209,8 +209,13 @@ def bench_dist_gpr(rank, world, device, n, single_gpu_ms=None, loss_pin=None, wa
                            panel=1024)
     if warm:
         _step(model)
+    from gptorch_b200 import _native as nv
     dg.WAIT_LOG = []
+    timer = nv.PhaseTimer()
+    nv.install_timer(timer)
     ms, loss = _timed(lambda: _step(model), 1, world, device)
+    nv.install_timer(None)
+    stages = timer.totals_ms()
     waits, dg.WAIT_LOG = dg.WAIT_LOG, None
     wait_ms = [a.elapsed_time(b) for a, b in waits]
     wait = torch.tensor([sum(wait_ms)], dtype=torch.float64, device=device)
@@ -224,6 +229,8 @@ def bench_dist_gpr(rank, world, device, n, single_gpu_ms=None, loss_pin=None, wa
            "frac_of_aggregate_fp64_peak": float(n) ** 3 / (ms / 1000.0) / 1e12 / (world * FP64_PEAK_TFLOPS),
            "collectives": "ncclBroadcast of each factored panel ((N - c) x 1024 doubles) in 3 sweeps (L, T = L^-1, Kinv), "
                           "all_reduce of a (N doubles) and of D + 2 gradient doubles",
+           "stage_ms_rank0": {k: v for k, v in sorted(stages.items()) if k.startswith("dist_")},
+           "stage_note": "dist_potrf / dist_trtri / dist_lauum are N^3/3 flop each, spread over the ranks",
            "panel_wait_ms_total_max_rank": wait.item(), "panel_waits": len(wait_ms),
            "panel_wait_ms_per_panel": wait.item() / max(3 * panels, 1),
            "max_mem_gb": torch.cuda.max_memory_allocated() / 1e9}

@@ -391,7 +391,7 @@ class DistGPRLogLikFn(Function):
 
     @staticmethod
     def forward(ctx, ops, kind, x, resid, ell, s2, noise, panel, group, side):
-        with torch.no_grad():
+        with torch.no_grad(), nv.phase("dist_potrf"):
             loglik, st = _factorise(ops, kind, x, resid, ell, s2, noise, panel, group, side)
         ctx.st = st
         ctx.save_for_backward(x, ell, s2)
@@ -404,9 +404,12 @@ class DistGPRLogLikFn(Function):
         if st is None:
             raise RuntimeError("DistGPRLogLikFn: the factor slabs were consumed by a previous backward pass")
         x, ell, s2 = ctx.saved_tensors
-        a = _invert_factor(st)
-        _inverse_from_t(st)
-        g_ell, g_s2, g_noise = _reduce_gradient(st, x, ell.reshape(-1), s2, a)
+        with nv.phase("dist_trtri"):
+            a = _invert_factor(st)
+        with nv.phase("dist_lauum"):
+            _inverse_from_t(st)
+        with nv.phase("dist_grad"):
+            g_ell, g_s2, g_noise = _reduce_gradient(st, x, ell.reshape(-1), s2, a)
         g = g.reshape(())
         need = ctx.needs_input_grad
         return (None, None, None,
