@@ -36,6 +36,7 @@ def ref_K(kind, X, X2, ell, s2):
     Xs = X / ell; X2s = (X if X2 is None else X2) / ell
     r2 = (Xs**2).sum(1, keepdim=True) + (X2s**2).sum(1, keepdim=True).t() - 2 * Xs @ X2s.t()
     r2 = r2.clamp_min(0)
+    if X2 is None: r2 = r2 * (1.0 - torch.eye(X.shape[0], dtype=r2.dtype, device=r2.device))   # exact zero self-distance
     if kind == 0: return s2 * torch.exp(-0.5 * r2)
     r = torch.sqrt(r2.clamp_min(1e-40))
     if kind == 1: return s2 * torch.exp(-r)
