@@ -766,7 +766,7 @@ def test_empty_and_single_point_inputs():
     assert mu.shape == (3, 2) and bool((var > 0).all())
 
 
-@pytest.mark.parametrize("d,dy,n", [(1, 1, 257), (33, 7, 300), (160, 2, 140), (9, 5, 129)])
+@pytest.mark.parametrize("d,dy,n", [(1, 1, 257), (33, 7, 300), (160, 2, 140), (9, 5, 129), (4, 9, 200), (32, 8, 130)])
 def test_gpr_wide_inputs_and_many_outputs(d, dy, n):
     """Input dimensions that are not multiples of the staging chunk (and the largest the backward kernel stages,
     D = 160), more outputs than one trsv group (4): loss and gradients against the oracle."""
