@@ -612,7 +612,7 @@ class GPRCompositeLogLikFn(Function):
 # ------------------------------------------------------------------------------------------------------
 # VFE sufficient statistics, streamed over row chunks of X
 # ------------------------------------------------------------------------------------------------------
-def kuu_condition_estimate(L, T, iters=8):
+def kuu_condition_estimate(L, T, iters=6):
     """Estimate of cond_2(Kuu) = lambda_max(L L^T) * lambda_max(T T^T) (T = L^-T) by two short power iterations on the
     native matrix-vector kernel.  Power iteration approaches each factor from below, so the result is a (slightly low)
     estimate; callers compare it with a threshold that leaves a safety margin."""

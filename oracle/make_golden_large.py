@@ -58,6 +58,18 @@ def gpr_large(n, out):
     out[nm + "/g_noise"] = gr["likelihood.variance"]
     out[nm + "/seconds"] = np.array(sec)
     print(nm, repr(loss.item()), "%.1f s" % sec, flush=True)
+    if n <= 8192:
+        predictions(model, nm, 8, out)
+
+
+def predictions(model, nm, d, out, n_test=48):
+    """model._predict on seeded test points: mean, variance (diag=True) and the full covariance."""
+    g = torch.Generator().manual_seed(777)
+    Xs = torch.rand(n_test, d, generator=g, dtype=torch.float64)
+    with torch.no_grad():
+        mu, var = model._predict(Xs, diag=True)
+        _, cov = model._predict(Xs, diag=False)
+    out[nm + "/pred_mean"], out[nm + "/pred_var"], out[nm + "/pred_cov"] = mu.numpy(), var.numpy().copy(), cov.numpy()
 
 
 def vfe_large(out, n=100000, d=16, m=1024):
@@ -78,6 +90,7 @@ def vfe_large(out, n=100000, d=16, m=1024):
     out[nm + "/seconds"] = np.array(sec)
     print(nm, repr(loss.item()), "%.1f s" % sec, flush=True)
     assert abs(loss.item() - 383333.82272224966) <= 1e-9 * 383333.8, "BASELINE.md section 3 pin moved"
+    predictions(model, nm, d, out)
 
 
 def svgp_large(out, n=65536, d=32, m=2048, batch=16384):
@@ -109,6 +122,7 @@ def svgp_large(out, n=65536, d=32, m=2048, batch=16384):
     out[nm + "/g_q_sqrt_raw_fro"] = np.array(np.linalg.norm(G))
     out[nm + "/seconds"] = np.array(sec)
     print(nm, repr(loss.item()), "%.1f s" % sec, flush=True)
+    predictions(model, nm, d, out)
 
 
 def main():

@@ -62,6 +62,31 @@ def test_row_sharding_and_grad_allreduce():
     assert t0 == t1 == 11.0
 
 
+def _distribute_syncs_parameters(rank, world):
+    """Every rank builds its model from its OWN shard and RNG state (different k-means centres, different q(u));
+    distribute() must leave all replicas with rank 0's parameter values."""
+    from gptorch_b200 import settings, kernels
+    from gptorch_b200.models import VFE
+    from gptorch_b200.param import Param
+    settings.set_default_device("cpu")
+    rng = np.random.RandomState(100 + rank)
+    X, Y = rng.rand(60, 2), rng.rand(60, 1)
+    np.random.seed(rank)
+    model = VFE(X, Y, kernels.Matern32(2, length_scales=0.5 + rank, variance=1.0 + rank), num_inducing_points=5)
+    model.extra = Param(torch.full((3,), float(rank + 7), dtype=torch.float64))
+    before = model.Z.detach().clone()
+    model.distribute()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    return before.numpy(), flat.numpy()
+
+
+def test_distribute_broadcasts_replicated_parameters():
+    (z0, p0), (z1, p1) = _run(_distribute_syncs_parameters)
+    assert not np.allclose(z0, z1)                  # the local initialisers really differ
+    assert np.array_equal(p0, p1)                   # ... and distribute() removes the difference
+    assert int(np.isclose(p0, 7.0).sum()) == 3 and not np.isclose(p0, 8.0).any()   # rank 0's values win
+
+
 def test_shard_rows_partitions():
     from gptorch_b200.dist import shard_rows
     for n, w in ((10, 3), (7, 8), (1000003, 8), (0, 2)):

@@ -273,6 +273,19 @@ def test_svgp_reference_known_answer(fixtures):
     assert cov.detach().cpu().numpy() == pytest.approx(exp_s)
 
 
+def _check_large_predictions(model, c, nm, d):
+    """model._predict on the seeded test points of oracle/make_golden_large.py against the unmodified reference."""
+    g = torch.Generator().manual_seed(777)
+    Xs = torch.rand(48, d, generator=g, dtype=torch.float64).cuda()
+    with torch.no_grad():
+        mu, var = model._predict(Xs, diag=True)
+        _, cov = model._predict(Xs, diag=False)
+    scale = np.abs(c.get(nm, "pred_cov")).max()
+    assert rel_err(mu.cpu().numpy(), c.get(nm, "pred_mean")) <= PRED_TOL
+    assert np.abs(var.cpu().numpy() - c.get(nm, "pred_var")).max() <= PRED_TOL * scale
+    assert np.abs(cov.cpu().numpy() - c.get(nm, "pred_cov")).max() <= PRED_TOL * scale
+
+
 def test_vfe_named_size_pin_n100000_m1024():
     """BASELINE.md section 3's VFE pin (N = 1e5, D = 16, M = 1024 -> 383333.82272224966) and every gradient of the
     unmodified reference at that size (oracle/make_golden_large.py)."""
@@ -400,6 +413,7 @@ def test_svgp_named_size_pin_m2048_b16384():
     assert rel_err(np.diag(G), c.get(nm, "g_q_sqrt_raw_diag")) <= GRAD_TOL
     assert rel_err(O.projections(G), c.get(nm, "g_q_sqrt_raw_proj")) <= GRAD_TOL
     assert abs(np.linalg.norm(G) - c.get(nm, "g_q_sqrt_raw_fro").item()) <= GRAD_TOL * c.get(nm, "g_q_sqrt_raw_fro").item()
+    _check_large_predictions(model, c, nm, d)
 
 
 @pytest.mark.parametrize("name", _SVGP.names + ["svgp_m2048_b16384"])

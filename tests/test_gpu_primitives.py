@@ -183,6 +183,16 @@ def test_gpr_loss_and_gradients_match_reference_at_scale(n):
     assert rel_err(model.kernel.variance.grad.cpu().numpy(), c.get(nm, "g_variance")) <= 1e-7
     assert rel_err(model.kernel.length_scales.grad.cpu().numpy(), c.get(nm, "g_length_scales")) <= 1e-7
     assert rel_err(model.likelihood.variance.grad.cpu().numpy(), c.get(nm, "g_noise")) <= 1e-7
+    if c.has(nm, "pred_mean"):      # GPR._predict at this size against the reference (mean, variance, full covariance)
+        g = torch.Generator().manual_seed(777)
+        Xs = torch.rand(48, 8, generator=g, dtype=torch.float64).cuda()
+        with torch.no_grad():
+            mu, var = model._predict(Xs, diag=True)
+            _, cov = model._predict(Xs, diag=False)
+        scale = np.abs(c.get(nm, "pred_cov")).max()
+        assert rel_err(mu.cpu().numpy(), c.get(nm, "pred_mean")) <= 1e-7
+        assert np.abs(var.cpu().numpy() - c.get(nm, "pred_var")).max() <= 1e-7 * scale
+        assert np.abs(cov.cpu().numpy() - c.get(nm, "pred_cov")).max() <= 1e-7 * scale
 
 
 def test_gpr_headline_config_matches_the_unmodified_reference_n32768():
