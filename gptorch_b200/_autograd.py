@@ -314,6 +314,8 @@ class CholeskyInverseFn(Function):
     def backward(ctx, G):
         L, dinv = ctx.saved_tensors
         Kinv, ctx.kinv = ctx.kinv, None
+        if Kinv is None:
+            raise RuntimeError("CholeskyInverseFn: the inverse was released by a previous backward pass")
         G = nv._c(G)
         S = nv._c(G + G.t())
         T = _tinv(nv._gemm_operand(L), dinv)
@@ -405,11 +407,15 @@ class SvgpMomentsFn(Function):
             q = nv.rowdot(KC, Kfu)
             mean = nv.gemv_n(Kfu, mvec)
         ctx.save_for_backward(Kfu, KC, mvec)
+        ctx.used = False
         return mean, q
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_mean, g_q):
+        if ctx.used:
+            raise RuntimeError("SvgpMomentsFn: the saved panel product was consumed by a previous backward pass")
+        ctx.used = True
         Kfu, KC, mvec = ctx.saved_tensors
         g_mean, g_q = nv._c(g_mean), nv._c(g_q).reshape(-1)
         b, m = Kfu.shape

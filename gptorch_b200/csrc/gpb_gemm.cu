@@ -13,6 +13,7 @@
 // slots and 12 LDS.64 per 32 DMMA, so shared-memory bandwidth and issue are far from limiting and the
 // k-permuted fragment addressing below is bank-conflict free under SWIZZLE_128B.
 #include "gpb_gemm.cuh"
+#include <cstdlib>
 
 namespace gpb {
 
@@ -408,12 +409,18 @@ static int launch_mode(const CUtensorMap& mapA, const CUtensorMap& mapB, const G
   // 128x128 tiles unless that would occupy fewer than ~half of the 148 SMs.
   const long t128 = static_cast<long>((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch;
   const long tiles = (a.flags & GF_LOWER_TILES) ? (t128 + a.batch * ((a.M + 127) / 128)) / 2 : t128;
+  static const long small_env = []() { const char* v = getenv("GPB_GEMM_SMALL_TILES"); return v && *v ? atol(v) : 0L; }();
+  // Lower-tile (SYRK) launches of up to ~2 waves of 128x128 tiles fill the 148 SMs better with 64x64 tiles (measured:
+  // m = 1536: 0.234 -> 0.193 ms, m = 3072: 1.27 -> 0.88 ms); full launches only below half a wave (NT/TN at 2048^3 are
+  // 1-2 % slower with small tiles).  GPB_GEMM_SMALL_TILES overrides both (tuning aid, read once).
+  const long small = small_env > 0 ? small_env
+                                   : ((a.flags & GF_LOWER_TILES) ? GEMM_SMALL_TILE_THRESHOLD_LOWER : GEMM_SMALL_TILE_THRESHOLD);
   if (a.flags & GF_ROWS_INPLACE) {
     if (a.N > 128) return GPB_ERR_BADARG;
     if (tiles <= GEMM_SMALL_TILE_THRESHOLD) return launch_cfg<MODE, CfgT>(mapA, mapB, kp, a, stream);
     return launch_cfg<MODE, CfgL>(mapA, mapB, kp, a, stream);
   }
-  if (tiles <= GEMM_SMALL_TILE_THRESHOLD) return launch_cfg<MODE, CfgS>(mapA, mapB, kp, a, stream);
+  if (tiles <= small) return launch_cfg<MODE, CfgS>(mapA, mapB, kp, a, stream);
   return launch_cfg<MODE, CfgL>(mapA, mapB, kp, a, stream);
 }
 

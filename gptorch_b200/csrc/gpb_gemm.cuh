@@ -39,6 +39,7 @@ struct GemmArgs {
 // operands (A of TN, B of TN/NN) boxes of 16 x 16.  Launches with at most GEMM_SMALL_TILE_THRESHOLD 128x128
 // tiles run with 64x64 tiles instead (4x the CTAs).
 constexpr int GEMM_SMALL_TILE_THRESHOLD = 64;
+constexpr int GEMM_SMALL_TILE_THRESHOLD_LOWER = 300;
 int gemm_launch(GemmMode mode, const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmArgs& args,
                 cudaStream_t stream);
 
