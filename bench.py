@@ -47,6 +47,10 @@ PIN_FILE = os.path.join(ROOT, "tests", "golden", "gpr_n32768_reference.json")
 # host-CPU cost of the reference between the sample size and the named size, measured on this pool's box (16 threads):
 # 7.79 s at N=12288 (BENCH_r01.json), 124.9 s at N=32768 (tests/golden/gpr_n32768_reference.json) -> exponent 2.83
 CPU_SCALING_EXPONENT = float(np.log(124.891459346 / 7.785708919) / np.log(32768.0 / 12288.0))
+# full-size seconds / sample seconds measured on this pool's box with the unmodified reference (16 threads): N=12288 7.79 and
+# 8.42 s (BENCH_r01.json, profiles/r02_bench_first.json), N=16384 18.57 s (profiles/r02_bench_reference_arm_first.json),
+# N=32768 124.89 s; sample sizes without a measured ratio fall back to the exponent
+CPU_FULL_OVER_SAMPLE = {12288: 124.891459346 / 8.10, 16384: 124.891459346 / 18.57}
 
 
 def parse():
@@ -145,7 +149,10 @@ def choose_cpu_sample(n_full, evals, budget_s, mods):
 
 
 def extrapolate(sec, sample_n, n_full):
-    scale = (n_full / float(sample_n)) ** CPU_SCALING_EXPONENT
+    if n_full == 32768 and sample_n in CPU_FULL_OVER_SAMPLE:
+        scale = CPU_FULL_OVER_SAMPLE[sample_n]
+    else:
+        scale = (n_full / float(sample_n)) ** CPU_SCALING_EXPONENT
     return sec * scale, scale
 
 
@@ -161,9 +168,9 @@ def cpu_baseline(n_full, sample_n=0):
     pin = reference_pin(n_full)
     out = {"value": 1.0 / full, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "reference",
            "sample": "unmodified cics-nd/gptorch (baseline/_ref, torch CPU fp64 / MKL, %d threads) loss+grad at N=%d, D=%d: "
-                     "%.2f s measured; scaled by (N/%d)^%.2f = %.1fx to N=%d (exponent measured on this pool between "
-                     "N=12288 and N=32768)" % (torch.get_num_threads(), sample_n, D_IN, sec, sample_n,
-                                               CPU_SCALING_EXPONENT, scale, n_full),
+                     "%.2f s measured; scaled by %.1fx to N=%d (the full-size / sample-size time ratio of the reference measured "
+                     "on this pool's host where available, else (N/%d)^%.2f)" % (
+                         torch.get_num_threads(), sample_n, D_IN, sec, scale, n_full, sample_n, CPU_SCALING_EXPONENT),
            "sample_n": sample_n, "sample_seconds": sec, "sample_loss": loss}
     if pin and "cpu" in pin:
         out["full_size_measured"] = {"seconds_per_eval": pin["cpu"]["seconds_best"], "threads": pin["cpu"]["threads"],
@@ -194,8 +201,9 @@ def run_reference(args, rank, world):
     value = 1.0 / full
     pin = reference_pin(args.n)
     sample = ("unmodified cics-nd/gptorch from baseline/_ref (torch CPU fp64 / MKL, %d threads): model.loss() + backward() "
-              "at N=%d timed %.2f s/step; value scaled by (N/%d)^%.2f = %.1fx to N=%d" % (
-                  torch.get_num_threads(), sample_n, sec, sample_n, CPU_SCALING_EXPONENT, scale, args.n))
+              "at N=%d timed %.2f s/step; value scaled by %.1fx to N=%d (the full-size / sample-size time ratio of the "
+              "reference measured on this pool's host where available, else (N/%d)^%.2f)" % (
+                  torch.get_num_threads(), sample_n, sec, scale, args.n, sample_n, CPU_SCALING_EXPONENT))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
