@@ -666,31 +666,38 @@ class VfeStatsFn(Function):
         dinv = _dinv_of(L)
         T = _tinv(Lc, dinv)
         n, m, dy = X.shape[0], Z.shape[0], Y.shape[1]
-        # The M x M Gram output has only (M/128)^2/2 tiles, far fewer than the GPU has SMs, so the long k = rows
-        # dimension is cut into VFE_SPLITS slices that accumulate into separate slots, summed at the end.
-        kper = VfeStatsFn._k_per_split(min(chunk, n))
         ldm = m + (m & 1)
-        AA3 = torch.zeros((VFE_SPLITS, m, ldm), dtype=torch.float64, device=X.device)
-        AYf = torch.zeros((m, dy), dtype=torch.float64, device=X.device)
         # Keep the streamed panels for the backward pass when they fit a modest budget (N*M*8 bytes <= 16 GiB of the
         # 180 GB); otherwise the backward pass rebuilds them chunk by chunk (one more covariance build, plus the solve in
         # the reference order).
         keep = any(ctx.needs_input_grad) and n * ldm * 8 <= VFE_PANEL_CACHE_BYTES
         cache = []
-        for s in range(0, n, chunk):
-            e = min(n, s + chunk)
-            P = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, None if phi_form else T)
-            if keep:
-                cache.append(P)
-            with nv.phase("vfe_gram"):
-                nv.gemm_splitk(nv.GEMM_TN, P, P, kper, AA3, beta=1.0, lower_only=True)
-                nv.gemv_t(P, Y[s:e], AYf, beta=1.0)
-            del P
-        AAf = AA3.sum(0)[:, :m]
-        AAf = torch.tril(AAf) + torch.tril(AAf, -1).t()
+        if phi_form:
+            # ONE native call streams the chunks: panel build, split-K Gram product, psi (gpb_kuf_stats_fwd)
+            with nv.phase("vfe_stats_fwd"):
+                AAf, AYf, kfu = nv.kuf_stats_fwd(kind, X, Y, Z, ell, sigma2, chunk, cache=keep)
+            cache = kfu
+        else:
+            # The M x M Gram output has only (M/128)^2/2 tiles, far fewer than the GPU has SMs, so the long k = rows
+            # dimension is cut into VFE_SPLITS slices that accumulate into separate slots, summed at the end.
+            kper = VfeStatsFn._k_per_split(min(chunk, n))
+            AA3 = torch.zeros((VFE_SPLITS, m, ldm), dtype=torch.float64, device=X.device)
+            AYf = torch.zeros((m, dy), dtype=torch.float64, device=X.device)
+            for s in range(0, n, chunk):
+                e = min(n, s + chunk)
+                P = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, T)
+                if keep:
+                    cache.append(P)
+                with nv.phase("vfe_gram"):
+                    nv.gemm_splitk(nv.GEMM_TN, P, P, kper, AA3, beta=1.0, lower_only=True)
+                    nv.gemv_t(P, Y[s:e], AYf, beta=1.0)
+                del P
+            AAf = AA3.sum(0)[:, :m]
+            AAf = torch.tril(AAf) + torch.tril(AAf, -1).t()
         # sum_i k(x_i, x_i) = n * sigma2 for a stationary kernel (gptorch/kernels.py:174-179); sum Y^2
         scal = torch.stack([sigma2.reshape(()) * float(n), nv.logdet_sumsq(None, Y)[1]])
         if group is not None:
+            AAf, AYf = AAf.contiguous(), AYf.contiguous()
             torch.distributed.all_reduce(AAf, group=group)
             torch.distributed.all_reduce(AYf, group=group)
             torch.distributed.all_reduce(scal, group=group)
@@ -701,7 +708,7 @@ class VfeStatsFn(Function):
                 AAf = 0.5 * (AAf + AAf.t())
                 AYf = nv.gemm(nv.GEMM_TN, T, AYf, flags=nv.GF_KHI_M)           # L^-1 psi
         ctx.kind, ctx.chunk, ctx.group, ctx.n_local, ctx.phi_form = kind, chunk, group, n, bool(phi_form)
-        ctx.panels = cache if keep else None
+        ctx.panels = cache if (keep and cache is not None and (phi_form or len(cache))) else None
         ctx.save_for_backward(X, Y, Z, ell, sigma2, T, AAf, AYf)
         return AAf, AYf, scal[0], scal[1]
 
@@ -734,27 +741,32 @@ class VfeStatsFn(Function):
         if phi:
             R = nv.gemm(nv.GEMM_NN, T, R, flags=nv.GF_KLO_M)   # L^-T S L^-1  (T[m][k] = 0 for k < m)
         w = nv.gemm(nv.GEMM_NN, T, gAY)          # L^-T gAY   (m x dy)
-        g_ell = torch.zeros_like(ell.reshape(-1))
-        g_s2 = torch.zeros(1, dtype=torch.float64, device=X.device)
-        gZ = torch.zeros_like(Z)
         panels, ctx.panels = ctx.panels, None
-        for ci, s in enumerate(range(0, n, chunk)):
-            e = min(n, s + chunk)
-            if panels is not None:
-                P = panels[ci]
-                panels[ci] = None
-            else:
-                P = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, None if phi else T)
-            with nv.phase("vfe_bwd_gemm"):
-                G = nv.gemm(nv.GEMM_NN, P, R)
-                nv.gemm(nv.GEMM_NT, Y[s:e], w, beta=1.0, C=G)
-            del P
-            with nv.phase("vfe_kern_bwd"):
-                ge, gs, gz = nv.kern_bwd(kind, X[s:e], Z, ell, sigma2, G, True)
-            del G
-            g_ell += ge
-            g_s2 += gs
-            gZ += gz
+        if phi:
+            with nv.phase("vfe_stats_bwd"):      # ONE native call re-streams the chunks (gpb_kuf_stats_bwd)
+                g_ell, g_s2, gZ = nv.kuf_stats_bwd(kind, X, Y, Z, ell, sigma2, chunk, R, w, kfu=panels)
+            del panels
+        else:
+            g_ell = torch.zeros_like(ell.reshape(-1))
+            g_s2 = torch.zeros(1, dtype=torch.float64, device=X.device)
+            gZ = torch.zeros_like(Z)
+            for ci, s in enumerate(range(0, n, chunk)):
+                e = min(n, s + chunk)
+                if panels is not None:
+                    P = panels[ci]
+                    panels[ci] = None
+                else:
+                    P = VfeStatsFn._panel(kind, X[s:e], Z, ell, sigma2, T)
+                with nv.phase("vfe_bwd_gemm"):
+                    G = nv.gemm(nv.GEMM_NN, P, R)
+                    nv.gemm(nv.GEMM_NT, Y[s:e], w, beta=1.0, C=G)
+                del P
+                with nv.phase("vfe_kern_bwd"):
+                    ge, gs, gz = nv.kern_bwd(kind, X[s:e], Z, ell, sigma2, G, True)
+                del G
+                g_ell += ge
+                g_s2 += gs
+                gZ += gz
         g_s2 += g_kd * float(ctx.n_local)
         if group is not None:
             flat = torch.cat([g_ell, g_s2, gZ.reshape(-1)])

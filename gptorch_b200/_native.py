@@ -468,6 +468,44 @@ def gemm_splitk(mode, A, B, k_per_split, C3, beta=1.0, alpha=1.0, lower_only=Fal
     return C3
 
 
+# ---------------------------------------------------------------------------------------------- streamed Kuf statistics
+def kuf_stats_fwd(kind, X, Y, Z, ell, sigma2, chunk, cache=False):
+    """(Phi = Kuf Kfu [m, m], psi = Kuf Y [m, dy], panel cache or None) streamed over row chunks of X in ONE native call."""
+    X, Y, Z = _c(X), _c(Y), _c(Z)
+    n, D = X.shape
+    m, dy = Z.shape[0], Y.shape[1]
+    ell = _c(ell).reshape(-1)
+    s2 = _c(sigma2).reshape(-1)
+    chunk = int(max(1, min(chunk, max(n, 1))))
+    ws = _ws(query("gpb_kuf_stats_workspace_bytes", m, D, dy, chunk), X.device)
+    Phi = _aligned_empty(m, m, X.device)[0]
+    psi = torch.empty((m, dy), dtype=torch.float64, device=X.device)
+    kfu = _aligned_empty(n, m, X.device)[0] if cache else None
+    call("gpb_kuf_stats_fwd", kind, ptr(X), n, X.stride(0), ptr(Y), dy, Y.stride(0), ptr(Z), m, Z.stride(0), D, ptr(ell),
+         ell.numel(), ptr(s2), chunk, ptr(Phi), Phi.stride(0), ptr(psi), psi.stride(0), ptr(kfu),
+         kfu.stride(0) if kfu is not None else 0, ptr(ws), ws.numel() * 8, stream_ptr())
+    return Phi[:, :m], psi, kfu
+
+
+def kuf_stats_bwd(kind, X, Y, Z, ell, sigma2, chunk, R, W, kfu=None):
+    """(g_ell, g_sigma2, gZ): the gradient Kfu_c R + Y_c W^T of every panel reduced against dK/d(ell, sigma2, Z)."""
+    X, Y, Z = _c(X), _c(Y), _c(Z)
+    n, D = X.shape
+    m, dy = Z.shape[0], Y.shape[1]
+    ell = _c(ell).reshape(-1)
+    s2 = _c(sigma2).reshape(-1)
+    R, W = _gemm_operand(R), _c(W)
+    chunk = int(max(1, min(chunk, max(n, 1))))
+    ws = _ws(query("gpb_kuf_stats_workspace_bytes", m, D, dy, chunk), X.device)
+    g_ell = torch.empty(ell.numel(), dtype=torch.float64, device=X.device)
+    g_s2 = torch.empty(1, dtype=torch.float64, device=X.device)
+    gZ = torch.empty((m, D), dtype=torch.float64, device=X.device)
+    call("gpb_kuf_stats_bwd", kind, ptr(X), n, X.stride(0), ptr(Y), dy, Y.stride(0), ptr(Z), m, Z.stride(0), D, ptr(ell),
+         ell.numel(), ptr(s2), chunk, ptr(R), R.stride(0), ptr(W), W.stride(0), ptr(kfu),
+         kfu.stride(0) if kfu is not None else 0, ptr(g_ell), ptr(g_s2), ptr(gZ), ptr(ws), ws.numel() * 8, stream_ptr())
+    return g_ell, g_s2, gZ
+
+
 # ---------------------------------------------------------------------------------------------- fused GPR gradient
 def gpr_grad(kind, X, ell, sigma2, Kinv, ldk, kd, a):
     """Returns (g_ell, g_sigma2, g_noise): d loss / d (ell, sigma2, sigma_n^2) for the GPR loss."""

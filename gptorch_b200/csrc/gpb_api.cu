@@ -1,5 +1,6 @@
 // gpb_api.cu -- the extern "C" boundary of libgpb200.so (declared in include/gpb200.h).
 #include "gpb_gemm.cuh"
+#include <algorithm>
 #include "../../include/gpb200.h"
 
 namespace gpb {
@@ -72,6 +73,31 @@ __global__ void __launch_bounds__(512) dmma_issue_probe_kernel(double* out, int 
 #pragma unroll
   for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- helpers of the streamed Kuf statistics (gpb_kuf_stats_fwd / _bwd) ------------------------------------------------
+constexpr int KUF_SPLITS = 16;   // k-slices of the streamed Gram product: the M x M output alone has too few tiles for 148 SMs
+
+// Phi[i][j] = sum_s slots[s][max(i,j)][min(i,j)]: sum the split-K slots (lower tiles valid) and mirror to a full matrix
+__global__ void kuf_reduce_sym_kernel(const double* __restrict__ slots, int splits, int m, long ldm, long slot_stride,
+                                      double* __restrict__ Phi, long ldphi) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= m) return;
+  const int r = i > j ? i : j, c = i > j ? j : i;
+  double s = 0.0;
+  for (int q = 0; q < splits; ++q) s += slots[q * slot_stride + static_cast<long>(r) * ldm + c];
+  Phi[static_cast<long>(i) * ldphi + j] = s;
+}
+
+__global__ void kuf_accumulate_kernel(double* __restrict__ dst, const double* __restrict__ src, long count) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] += src[i];
+}
+
+static inline size_t kuf_align(size_t b) { return (b + 255) / 256 * 256; }
+static inline int kuf_k_per_split(int rows) {
+  const int per = (rows + KUF_SPLITS - 1) / KUF_SPLITS;
+  return std::max(16, (per + 15) / 16 * 16);
 }
 
 #pragma GCC visibility push(default)
@@ -237,6 +263,118 @@ int gpb_gemm_splitk(int mode, int m, int n, int k_total, int k_per_split, double
   else { g.dax = k_per_split; g.dby = k_per_split; }
   g.flags = lower_only ? GF_LOWER_TILES : 0u;
   return gemm_launch(gm, mapA, mapB, g, S(stream));
+}
+
+// Workspace: [panel chunk x ldm][G chunk x ldm][split slots S x m x ldm][kern_bwd scratch][gemv_t scratch][small temporaries]
+size_t gpb_kuf_stats_workspace_bytes(int m, int D, int dy, int chunk_rows) {
+  if (m <= 0 || D <= 0 || dy <= 0 || chunk_rows <= 0) return 0;
+  const size_t ldm = static_cast<size_t>(m) + (m & 1);
+  size_t b = 2 * kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
+  b += kuf_align(static_cast<size_t>(KUF_SPLITS) * m * ldm * 8);
+  b += kuf_align(kern_bwd_workspace_bytes(chunk_rows, m, D));
+  b += kuf_align(gemv_t_workspace_bytes(chunk_rows, m));
+  b += kuf_align((static_cast<size_t>(D) + 1 + static_cast<size_t>(m) * D) * 8);
+  return b;
+}
+
+int gpb_kuf_stats_fwd(int kind, const double* X, long n, long ldx, const double* Y, int dy, long ldy, const double* Z,
+                      int m, long ldz, int D, const double* ell, int ell_len, const double* sigma2, int chunk_rows,
+                      double* Phi, long ldphi, double* psi, long ldpsi, double* kfu_cache, long ldcache,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || m <= 0 || D <= 0 || dy <= 0 || chunk_rows <= 0) return GPB_ERR_BADARG;
+  if (!X || !Y || !Z || !ell || !sigma2 || !Phi || !psi || ldphi < m || ldpsi < dy) return GPB_ERR_BADARG;
+  if (kfu_cache && (ldcache < m || (ldcache & 1) || (reinterpret_cast<uintptr_t>(kfu_cache) & 15))) return GPB_ERR_ALIGN;
+  if (!workspace || workspace_bytes < gpb_kuf_stats_workspace_bytes(m, D, dy, chunk_rows)) return GPB_ERR_BADARG;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return GPB_ERR_ALIGN;
+  const long ldm = m + (m & 1);
+  char* w = static_cast<char*>(workspace);
+  double* panel = reinterpret_cast<double*>(w);
+  w += 2 * kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
+  double* slots = reinterpret_cast<double*>(w);
+  w += kuf_align(static_cast<size_t>(KUF_SPLITS) * m * ldm * 8);
+  w += kuf_align(kern_bwd_workspace_bytes(chunk_rows, m, D));
+  void* gemv_ws = w;
+  const size_t gemv_bytes = gemv_t_workspace_bytes(chunk_rows, m);
+  cudaStream_t st = S(stream);
+  const long slot_stride = static_cast<long>(m) * ldm;
+  GPB_CUDA_CHECK(cudaMemsetAsync(slots, 0, static_cast<size_t>(KUF_SPLITS) * slot_stride * 8, st));
+  for (int o = 0; o < dy; ++o)
+    GPB_CUDA_CHECK(cudaMemset2DAsync(psi + o, ldpsi * 8, 0, 8, m, st));
+  const int kper = kuf_k_per_split(static_cast<int>(std::min<long>(chunk_rows, std::max<long>(n, 1))));
+  for (long s0 = 0; s0 < n; s0 += chunk_rows) {
+    const int rows = static_cast<int>(std::min<long>(chunk_rows, n - s0));
+    double* P = kfu_cache ? kfu_cache + s0 * ldcache : panel;
+    const long ldp = kfu_cache ? ldcache : ldm;
+    int rc = gpb_kern_fwd(kind, X + s0 * ldx, rows, ldx, Z, m, ldz, D, ell, ell_len, sigma2, nullptr, 0, P, ldp, stream);
+    if (rc) return rc;
+    rc = gpb_gemm_splitk(GEMM_TN, m, m, rows, kper, 1.0, P, ldp, P, ldp, 1.0, slots, ldm, slot_stride, 1, stream);
+    if (rc) return rc;
+    rc = gpb_gemv_t(P, rows, m, ldp, Y + s0 * ldy, dy, ldy, 1.0, psi, ldpsi, gemv_ws, gemv_bytes, stream);
+    if (rc) return rc;
+  }
+  dim3 grid((m + 255) / 256, m);
+  kuf_reduce_sym_kernel<<<grid, 256, 0, st>>>(slots, KUF_SPLITS, m, ldm, slot_stride, Phi, ldphi);
+  count_launch();
+  GPB_CUDA_CHECK(cudaGetLastError());
+  return GPB_OK;
+}
+
+int gpb_kuf_stats_bwd(int kind, const double* X, long n, long ldx, const double* Y, int dy, long ldy, const double* Z,
+                      int m, long ldz, int D, const double* ell, int ell_len, const double* sigma2, int chunk_rows,
+                      const double* R, long ldr, const double* W, long ldw, const double* kfu_cache, long ldcache,
+                      double* g_ell, double* g_sigma2, double* gZ, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (n < 0 || m <= 0 || D <= 0 || dy <= 0 || chunk_rows <= 0) return GPB_ERR_BADARG;
+  if (!X || !Y || !Z || !ell || !sigma2 || !R || !W || !g_ell || !g_sigma2 || !gZ) return GPB_ERR_BADARG;
+  if (ldr < m || (ldr & 1) || (reinterpret_cast<uintptr_t>(R) & 15)) return GPB_ERR_ALIGN;
+  if (kfu_cache && (ldcache < m || (ldcache & 1) || (reinterpret_cast<uintptr_t>(kfu_cache) & 15))) return GPB_ERR_ALIGN;
+  if (!workspace || workspace_bytes < gpb_kuf_stats_workspace_bytes(m, D, dy, chunk_rows)) return GPB_ERR_BADARG;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return GPB_ERR_ALIGN;
+  const long ldm = m + (m & 1);
+  char* w = static_cast<char*>(workspace);
+  double* panel = reinterpret_cast<double*>(w);
+  w += kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
+  double* G = reinterpret_cast<double*>(w);
+  w += kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
+  w += kuf_align(static_cast<size_t>(KUF_SPLITS) * m * ldm * 8);
+  void* kb_ws = w;
+  const size_t kb_bytes = kern_bwd_workspace_bytes(chunk_rows, m, D);
+  w += kuf_align(kb_bytes);
+  w += kuf_align(gemv_t_workspace_bytes(chunk_rows, m));
+  double* t_ell = reinterpret_cast<double*>(w);
+  double* t_s2 = t_ell + D;
+  double* t_z = t_s2 + 1;
+  cudaStream_t st = S(stream);
+  GPB_CUDA_CHECK(cudaMemsetAsync(g_ell, 0, static_cast<size_t>(ell_len) * 8, st));
+  GPB_CUDA_CHECK(cudaMemsetAsync(g_sigma2, 0, 8, st));
+  GPB_CUDA_CHECK(cudaMemsetAsync(gZ, 0, static_cast<size_t>(m) * D * 8, st));
+  // Y_c W^T needs the right-hand sides as a K-contiguous operand: Y rows (dy values, stride ldy) may be odd-strided, so
+  // the rank-dy update runs through the in-place row kernel instead of the TMA GEMM
+  for (long s0 = 0; s0 < n; s0 += chunk_rows) {
+    const int rows = static_cast<int>(std::min<long>(chunk_rows, n - s0));
+    const double* P;
+    long ldp;
+    if (kfu_cache) {
+      P = kfu_cache + s0 * ldcache; ldp = ldcache;
+    } else {
+      int rc = gpb_kern_fwd(kind, X + s0 * ldx, rows, ldx, Z, m, ldz, D, ell, ell_len, sigma2, nullptr, 0, panel, ldm, stream);
+      if (rc) return rc;
+      P = panel; ldp = ldm;
+    }
+    int rc = gpb_gemm(GEMM_NN, rows, m, m, 1.0, P, ldp, R, ldr, 0.0, G, ldm, 0, stream);            // Kfu_c R
+    if (rc) return rc;
+    rc = gpb_rows_scale_add_outer(G, rows, m, ldm, nullptr, 1.0, Y + s0 * ldy, dy, ldy, W, ldw, stream);   // + Y_c W^T
+    if (rc) return rc;
+    rc = gpb_kern_bwd(kind, X + s0 * ldx, rows, ldx, Z, m, ldz, D, ell, ell_len, sigma2, G, ldm, 0, t_ell, t_s2, t_z,
+                      kb_ws, kb_bytes, stream);
+    if (rc) return rc;
+    kuf_accumulate_kernel<<<(ell_len + 255) / 256, 256, 0, st>>>(g_ell, t_ell, ell_len);
+    kuf_accumulate_kernel<<<1, 32, 0, st>>>(g_sigma2, t_s2, 1);
+    kuf_accumulate_kernel<<<(m * D + 255) / 256, 256, 0, st>>>(gZ, t_z, static_cast<long>(m) * D);
+    count_launch(3);
+    GPB_CUDA_CHECK(cudaGetLastError());
+  }
+  return GPB_OK;
 }
 
 size_t gpb_gpr_grad_workspace_bytes(int n, int D) { return gpr_grad_workspace_bytes(n, D); }

@@ -219,6 +219,28 @@ int gpb_gemm_splitk(int mode, int m, int n, int k_total, int k_per_split, double
                     const double* B, long ldb, double beta, double* C, long ldc, long c_split_stride, int lower_only,
                     void* stream);
 
+/* ---- streamed Kuf statistics of the sparse models ---------------------------------------------------------------
+ * Phi = Kuf Kfu (M x M, full symmetric) and psi = Kuf Y (M x dy) for Kfu = K(X, Z), accumulated over row chunks of X
+ * without ever holding the N x M matrix: per chunk the covariance panel is built (gpb_kern_fwd), its Gram product is
+ * accumulated by the split-K TN GEMM and psi by the transposed panel-vector kernel.  Replaces Kuf = K(Z, x) and the
+ * products A @ A.t(), A @ err of VFE.log_likelihood (gptorch/models/sparse_gpr.py:126-137) in the form with the M x M
+ * congruence applied afterwards (A A^T = L^-1 Phi L^-T); it is also the quantity a row-sharded run all-reduces.
+ *   chunk_rows: rows of X per panel;  kfu_cache: optional N x ldcache buffer that receives every panel (NULL = the panels
+ *   are rebuilt by the backward call);  workspace: gpb_kuf_stats_workspace_bytes(m, D, dy, chunk_rows).
+ * The backward call reduces the gradient with respect to the panels, dLoss/dKfu_c = Kfu_c R + Y_c W^T with
+ * R = dLoss/dPhi + (dLoss/dPhi)^T (M x M, symmetric) and W = dLoss/dpsi (M x dy), against dK/d(ell, sigma2, Z):
+ *   g_ell (ell_len), g_sigma2 (1) and gZ (M x D, dense) are OVERWRITTEN with the sums over all chunks. */
+size_t gpb_kuf_stats_workspace_bytes(int m, int D, int dy, int chunk_rows);
+int gpb_kuf_stats_fwd(int kind, const double* X, long n, long ldx, const double* Y, int dy, long ldy, const double* Z,
+                      int m, long ldz, int D, const double* ell, int ell_len, const double* sigma2, int chunk_rows,
+                      double* Phi, long ldphi, double* psi, long ldpsi, double* kfu_cache, long ldcache,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int gpb_kuf_stats_bwd(int kind, const double* X, long n, long ldx, const double* Y, int dy, long ldy, const double* Z,
+                      int m, long ldz, int D, const double* ell, int ell_len, const double* sigma2, int chunk_rows,
+                      const double* R, long ldr, const double* W, long ldw, const double* kfu_cache, long ldcache,
+                      double* g_ell, double* g_sigma2, double* gZ, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ---- fused GPR gradient ------------------------------------------------------------------------------------
  * Given Kinv in the blocked form left by gpb_potri_lower and a = Ky^-1 (y - m) (n x dy, lda_a), reduce
  *    W = 1/2 (dy * Kinv - a a^T)            (dLoss/dKy; gptorch/models/gpr.py:47-67)
