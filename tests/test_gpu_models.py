@@ -345,6 +345,41 @@ def test_vfe_phi_form_meets_the_parity_tolerances(name):
     assert rel_err(gr["Z"], c.get(name, "g_Z")) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("chunk", [1000, 999, 64])
+def test_vfe_streaming_over_many_ragged_chunks_and_outputs(chunk, monkeypatch):
+    """The streamed statistics (gpb_kuf_stats_fwd / _bwd and the reference-order loop) over MANY row chunks with a ragged
+    last chunk, several outputs and with / without the panel cache: both forms against the oracle on the same data."""
+    from oracle import gp_oracle as O
+    from gptorch_b200 import kernels, likelihoods, settings, _autograd as ag
+    from gptorch_b200.models import VFE, sparse_gpr
+    n, d, m, dy = 4321, 5, 37, 3
+    X, Y1, g = O.synth_regression(n, d)
+    Y = torch.cat([Y1 * (1.0 + 0.5 * k) + 0.05 * k for k in range(dy)], dim=1)
+    Z = O.synth_inducing(X, m, g)
+    ell = 0.5 + 0.1 * np.arange(d)
+    h = O.Hyper("Matern52", ell, 1.3, 0.05)
+    Zp = Z.clone().requires_grad_(True)
+    ref = -O.vfe_elbo(h, X, Y, Zp)
+    ref.backward()
+    monkeypatch.setattr(sparse_gpr, "VFE_CHUNK_ROWS", chunk)
+    for form in (True, False):
+        for budget in (ag.VFE_PANEL_CACHE_BYTES, 0):
+            monkeypatch.setattr(ag, "VFE_PANEL_CACHE_BYTES", budget)
+            model = VFE(X.numpy(), Y.numpy(), kernels.Matern52(d, ARD=True, length_scales=ell.copy(), variance=1.3),
+                        inducing_points=Z.numpy(), likelihood=likelihoods.Gaussian(variance=0.05))
+            settings.vfe_phi_form = form
+            try:
+                loss = model.loss()
+                loss.backward()
+            finally:
+                settings.vfe_phi_form = "auto"
+            assert rel_err(loss.item(), ref.item()) <= LML_TOL, (form, budget)
+            assert rel_err(model.Z.grad.cpu().numpy(), Zp.grad.numpy()) <= GRAD_TOL, (form, budget)
+            assert rel_err(model.kernel.length_scales.grad.cpu().numpy(), h.raw_ell.grad.numpy()) <= GRAD_TOL, (form, budget)
+            assert rel_err(model.kernel.variance.grad.cpu().numpy(), h.raw_var.grad.numpy()) <= GRAD_TOL, (form, budget)
+            assert rel_err(model.likelihood.variance.grad.cpu().numpy(), h.raw_noise.grad.numpy()) <= GRAD_TOL, (form, budget)
+
+
 def test_vfe_phi_form_is_gated_by_the_conditioning_of_kuu():
     """"auto": the Phi form is used only when the estimated cond_2(Kuu) is below settings.vfe_phi_cond_max.  The
     estimate (two power iterations on the native matvec) is checked against the exact condition number; an
