@@ -107,7 +107,23 @@ class NativeOps:
         Lc = nv._gemm_operand(Lpp)
         return ag._tinv(Lc, nv.tri_diag_inverse(Lc))
 
+    SPLITK_MIN_K = 4096      # TN products with a long reduction and too few output tiles for 148 SMs are k-sliced
+
     def gemm(self, mode, A, B, alpha=1.0, beta=0.0, C=None, flags=0):
+        if mode == nv.GEMM_TN and C is not None and alpha == 1.0 and beta == 0.0 and flags == 0:
+            # Ky^-1 = T^T T, block row i: the output is only (panel width / 128) x (owned columns / 128) tiles while the
+            # reduction runs over all rows below -- early block rows would occupy a fraction of the GPU for a long time
+            k, m = A.shape
+            n = B.shape[1]
+            tiles = ((m + 127) // 128) * ((n + 127) // 128)
+            if tiles < 2 * 148 and k >= self.SPLITK_MIN_K:
+                splits = int(min(16, max(2, (4 * 148 + tiles - 1) // tiles)))
+                kper = ((k + splits - 1) // splits + 15) // 16 * 16
+                ldn = n + (n & 1)
+                C3 = torch.zeros((splits, m, ldn), dtype=torch.float64, device=A.device)
+                nv.gemm_splitk(mode, A, B, kper, C3, beta=0.0)
+                torch.sum(C3[:, :, :n], dim=0, out=C) if C.is_contiguous() else C.copy_(C3[:, :, :n].sum(0))
+                return C
         return nv.gemm(mode, A, B, alpha=alpha, beta=beta, C=C, flags=flags)
 
     def gemv_t(self, A, Y, out):

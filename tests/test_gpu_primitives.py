@@ -314,3 +314,26 @@ def test_triangular_inverse_and_syrk_nodes_match_autograd():
     assert rel_err(T.detach().cpu().numpy(), Tr.detach().numpy()) < 1e-10
     assert rel_err(C.detach().cpu().numpy(), (Tr @ Tr.t()).detach().numpy()) < 1e-10
     assert rel_err(torch.tril(Lc.grad).cpu().numpy(), torch.tril(Lr.grad).numpy()) < 1e-8
+
+
+def test_distributed_ops_split_long_reductions():
+    """NativeOps.gemm (gptorch_b200/models/dist_gpr.py) k-slices TN products whose output has too few tiles for the GPU
+    (the early block rows of Ky^-1 = T^T T); the result must equal the plain product."""
+    from gptorch_b200.models.dist_gpr import NativeOps
+    from gptorch_b200 import _native as nv
+    ops = NativeOps()
+    g = torch.Generator().manual_seed(12)
+    for k, m, n in ((5000, 256, 384), (4096, 130, 77), (9001, 1024, 129)):
+        A = torch.randn(k, m, generator=g, dtype=torch.float64).cuda()
+        B = torch.randn(k, n, generator=g, dtype=torch.float64).cuda()
+        buf = nv._aligned_empty(m, n, A.device)[0]
+        C = buf[:, :n]
+        nv.reset_launch_count()
+        ops.gemm(ops.GEMM_TN, A, B, C=C)
+        assert nv.launch_count() == 1                                   # one batched split-K launch
+        assert rel_err(C.cpu().numpy(), (A.t() @ B).cpu().numpy()) < 1e-12
+    A = torch.randn(300, 256, generator=g, dtype=torch.float64).cuda()      # short reduction: plain product
+    B = torch.randn(300, 128, generator=g, dtype=torch.float64).cuda()
+    C = nv._aligned_empty(256, 128, A.device)[0][:, :128]
+    ops.gemm(ops.GEMM_TN, A, B, C=C)
+    assert rel_err(C.cpu().numpy(), (A.t() @ B).cpu().numpy()) < 1e-12
