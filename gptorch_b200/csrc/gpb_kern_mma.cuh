@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(BM_THREADS, (DP <= 16 ? 2 : 1)) kern_bwd_mma_k
   double* wS = red + 32;                 // [8][DP]  per-warp S_d
   double* vs = wS + 8 * DP;              // [2][128] per-warp-row column sums
   double* ellv = vs + 2 * 128;           // [DP]
-  double* acol = ellv + DP;              // [128][BM_DY]  a_j  (GPR only)
-  double* arow = acol + 128 * BM_DY;     // [64][BM_DY]   a_i  (GPR only)
+  double* acol = ellv + DP;              // [BM_DY][128]  a_j  (GPR only; output-major: conflict-free fragment reads)
+  double* arow = acol + 128 * BM_DY;     // [BM_DY][64]   a_i  (GPR only)
   double* Hs = Gs;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(BM_THREADS, (DP <= 16 ? 2 : 1)) kern_bwd_mma_k
   }
   if (GPR) {
     for (int idx = t; idx < 128 * BM_DY; idx += BM_THREADS) {
-      const int cc = idx / BM_DY, o = idx - cc * BM_DY;
+      const int o = idx >> 7, cc = idx & 127;
       acol[idx] = (c0 + cc < p.n2 && o < dy) ? p.a[static_cast<long>(c0 + cc) * p.lda + o] : 0.0;
     }
   }
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(BM_THREADS, (DP <= 16 ? 2 : 1)) kern_bwd_mma_k
     }
     if (GPR) {
       for (int idx = t; idx < 64 * BM_DY; idx += BM_THREADS) {
-        const int rr = idx / BM_DY, o = idx - rr * BM_DY;
+        const int o = idx >> 6, rr = idx & 63;
         arow[idx] = (m0 + rr < p.n1 && o < dy) ? p.a[static_cast<long>(m0 + rr) * p.lda + o] : 0.0;
       }
     }
@@ -187,6 +187,21 @@ __global__ void __launch_bounds__(BM_THREADS, (DP <= 16 ? 2 : 1)) kern_bwd_mma_k
         const int row = m0 + lr;
         const double nrow = na[lr];
         double us = 0.0;
+        double aa[4][2];
+        if (GPR) {
+          // a_i . a_j for the 8 elements of this fragment row: one pass over the outputs, row value loaded once
+#pragma unroll
+          for (int j = 0; j < 4; ++j) aa[j][0] = aa[j][1] = 0.0;
+          for (int o = 0; o < dy; ++o) {
+            const double ar = arow[o * 64 + lr];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double2 ac = *reinterpret_cast<const double2*>(acol + o * 128 + wn * 32 + 8 * j + 2 * kk);
+              aa[j][0] = fma(ar, ac.x, aa[j][0]);
+              aa[j][1] = fma(ar, ac.y, aa[j][1]);
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const double2 g2v = *reinterpret_cast<const double2*>(Gs + lr * BM_HLD + wn * 32 + 8 * j + 2 * kk);
@@ -202,10 +217,8 @@ __global__ void __launch_bounds__(BM_THREADS, (DP <= 16 ? 2 : 1)) kern_bwd_mma_k
             kern_base_fac(KIND, r2, kbase, fac1);
             double g = e ? g2v.y : g2v.x;
             if (GPR) {
-              double aa = 0.0;
-              for (int o = 0; o < dy; ++o) aa += arow[lr * BM_DY + o] * acol[lc * BM_DY + o];
               const bool valid = row < p.n1 && col < p.n2 && col <= row;
-              const double w = valid ? 0.5 * (static_cast<double>(dy) * g - aa) : 0.0;
+              const double w = valid ? 0.5 * (static_cast<double>(dy) * g - aa[j][e]) : 0.0;
               gn += diag ? w : 0.0;
               g = diag ? w : 2.0 * w;
             }
