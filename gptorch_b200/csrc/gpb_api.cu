@@ -1,5 +1,8 @@
 // gpb_api.cu -- the extern "C" boundary of libgpb200.so (declared in include/gpb200.h).
 #include "gpb_gemm.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 #include <algorithm>
 #include "../../include/gpb200.h"
 
@@ -95,6 +98,32 @@ __global__ void kuf_accumulate_kernel(double* __restrict__ dst, const double* __
 }
 
 static inline size_t kuf_align(size_t b) { return (b + 255) / 256 * 256; }
+
+// Two-stage software pipeline over the row chunks: the tensor-pipe-bound GEMM stage of chunk c runs on the caller's
+// stream while the covariance build (forward) or the covariance backward (adjoint) of a neighbouring chunk runs on a
+// high-priority side stream, double-buffered.  One side stream + event set per (device, caller stream).
+struct KufAux {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, ready[2] = {nullptr, nullptr}, free_[2] = {nullptr, nullptr};
+};
+
+static int kuf_aux(cudaStream_t caller, KufAux** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, KufAux> table;
+  int dev = 0;
+  GPB_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  KufAux& a = table[std::make_pair(dev, caller)];
+  if (a.side == nullptr) {
+    int lo = 0, hi = 0;
+    GPB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GPB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.side, cudaStreamNonBlocking, hi));
+    cudaEvent_t* evs[] = {&a.fork, &a.join, &a.ready[0], &a.ready[1], &a.free_[0], &a.free_[1]};
+    for (cudaEvent_t* e : evs) GPB_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  *out = &a;
+  return GPB_OK;
+}
 static inline int kuf_k_per_split(int rows) {
   const int per = (rows + KUF_SPLITS - 1) / KUF_SPLITS;
   return std::max(16, (per + 15) / 16 * 16);
@@ -265,11 +294,11 @@ int gpb_gemm_splitk(int mode, int m, int n, int k_total, int k_per_split, double
   return gemm_launch(gm, mapA, mapB, g, S(stream));
 }
 
-// Workspace: [panel chunk x ldm][G chunk x ldm][split slots S x m x ldm][kern_bwd scratch][gemv_t scratch][small temporaries]
+// Workspace: [3 chunk x ldm buffers][split slots S x m x ldm][kern_bwd scratch][gemv_t scratch][small temporaries]
 size_t gpb_kuf_stats_workspace_bytes(int m, int D, int dy, int chunk_rows) {
   if (m <= 0 || D <= 0 || dy <= 0 || chunk_rows <= 0) return 0;
   const size_t ldm = static_cast<size_t>(m) + (m & 1);
-  size_t b = 2 * kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
+  size_t b = 3 * kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);       // two pipeline buffers + one panel
   b += kuf_align(static_cast<size_t>(KUF_SPLITS) * m * ldm * 8);
   b += kuf_align(kern_bwd_workspace_bytes(chunk_rows, m, D));
   b += kuf_align(gemv_t_workspace_bytes(chunk_rows, m));
@@ -287,30 +316,43 @@ int gpb_kuf_stats_fwd(int kind, const double* X, long n, long ldx, const double*
   if (!workspace || workspace_bytes < gpb_kuf_stats_workspace_bytes(m, D, dy, chunk_rows)) return GPB_ERR_BADARG;
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return GPB_ERR_ALIGN;
   const long ldm = m + (m & 1);
+  const size_t chunk_bytes = kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
   char* w = static_cast<char*>(workspace);
-  double* panel = reinterpret_cast<double*>(w);
-  w += 2 * kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
+  double* pbuf[2] = {reinterpret_cast<double*>(w), reinterpret_cast<double*>(w + chunk_bytes)};
+  w += 3 * chunk_bytes;
   double* slots = reinterpret_cast<double*>(w);
   w += kuf_align(static_cast<size_t>(KUF_SPLITS) * m * ldm * 8);
   w += kuf_align(kern_bwd_workspace_bytes(chunk_rows, m, D));
   void* gemv_ws = w;
   const size_t gemv_bytes = gemv_t_workspace_bytes(chunk_rows, m);
   cudaStream_t st = S(stream);
+  KufAux* aux = nullptr;
+  if (int rc = kuf_aux(st, &aux)) return rc;
   const long slot_stride = static_cast<long>(m) * ldm;
   GPB_CUDA_CHECK(cudaMemsetAsync(slots, 0, static_cast<size_t>(KUF_SPLITS) * slot_stride * 8, st));
   for (int o = 0; o < dy; ++o)
     GPB_CUDA_CHECK(cudaMemset2DAsync(psi + o, ldpsi * 8, 0, 8, m, st));
   const int kper = kuf_k_per_split(static_cast<int>(std::min<long>(chunk_rows, std::max<long>(n, 1))));
-  for (long s0 = 0; s0 < n; s0 += chunk_rows) {
+  GPB_CUDA_CHECK(cudaEventRecord(aux->fork, st));
+  GPB_CUDA_CHECK(cudaStreamWaitEvent(aux->side, aux->fork, 0));
+  long c = 0;
+  for (long s0 = 0; s0 < n; s0 += chunk_rows, ++c) {
     const int rows = static_cast<int>(std::min<long>(chunk_rows, n - s0));
-    double* P = kfu_cache ? kfu_cache + s0 * ldcache : panel;
+    const int b = static_cast<int>(c & 1);
+    double* P = kfu_cache ? kfu_cache + s0 * ldcache : pbuf[b];
     const long ldp = kfu_cache ? ldcache : ldm;
-    int rc = gpb_kern_fwd(kind, X + s0 * ldx, rows, ldx, Z, m, ldz, D, ell, ell_len, sigma2, nullptr, 0, P, ldp, stream);
+    // side stream: covariance panel of this chunk (its buffer must have been consumed by the Gram product of chunk c - 2)
+    if (!kfu_cache && c >= 2) GPB_CUDA_CHECK(cudaStreamWaitEvent(aux->side, aux->free_[b], 0));
+    int rc = gpb_kern_fwd(kind, X + s0 * ldx, rows, ldx, Z, m, ldz, D, ell, ell_len, sigma2, nullptr, 0, P, ldp, aux->side);
     if (rc) return rc;
+    GPB_CUDA_CHECK(cudaEventRecord(aux->ready[b], aux->side));
+    // caller's stream: Gram product and psi of this chunk
+    GPB_CUDA_CHECK(cudaStreamWaitEvent(st, aux->ready[b], 0));
     rc = gpb_gemm_splitk(GEMM_TN, m, m, rows, kper, 1.0, P, ldp, P, ldp, 1.0, slots, ldm, slot_stride, 1, stream);
     if (rc) return rc;
     rc = gpb_gemv_t(P, rows, m, ldp, Y + s0 * ldy, dy, ldy, 1.0, psi, ldpsi, gemv_ws, gemv_bytes, stream);
     if (rc) return rc;
+    GPB_CUDA_CHECK(cudaEventRecord(aux->free_[b], st));
   }
   dim3 grid((m + 255) / 256, m);
   kuf_reduce_sym_kernel<<<grid, 256, 0, st>>>(slots, KUF_SPLITS, m, ldm, slot_stride, Phi, ldphi);
@@ -331,11 +373,11 @@ int gpb_kuf_stats_bwd(int kind, const double* X, long n, long ldx, const double*
   if (!workspace || workspace_bytes < gpb_kuf_stats_workspace_bytes(m, D, dy, chunk_rows)) return GPB_ERR_BADARG;
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return GPB_ERR_ALIGN;
   const long ldm = m + (m & 1);
+  const size_t chunk_bytes = kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
   char* w = static_cast<char*>(workspace);
-  double* panel = reinterpret_cast<double*>(w);
-  w += kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
-  double* G = reinterpret_cast<double*>(w);
-  w += kuf_align(static_cast<size_t>(chunk_rows) * ldm * 8);
+  double* gbuf[2] = {reinterpret_cast<double*>(w), reinterpret_cast<double*>(w + chunk_bytes)};
+  double* panel = reinterpret_cast<double*>(w + 2 * chunk_bytes);
+  w += 3 * chunk_bytes;
   w += kuf_align(static_cast<size_t>(KUF_SPLITS) * m * ldm * 8);
   void* kb_ws = w;
   const size_t kb_bytes = kern_bwd_workspace_bytes(chunk_rows, m, D);
@@ -345,13 +387,20 @@ int gpb_kuf_stats_bwd(int kind, const double* X, long n, long ldx, const double*
   double* t_s2 = t_ell + D;
   double* t_z = t_s2 + 1;
   cudaStream_t st = S(stream);
+  KufAux* aux = nullptr;
+  if (int rc = kuf_aux(st, &aux)) return rc;
   GPB_CUDA_CHECK(cudaMemsetAsync(g_ell, 0, static_cast<size_t>(ell_len) * 8, st));
   GPB_CUDA_CHECK(cudaMemsetAsync(g_sigma2, 0, 8, st));
   GPB_CUDA_CHECK(cudaMemsetAsync(gZ, 0, static_cast<size_t>(m) * D * 8, st));
-  // Y_c W^T needs the right-hand sides as a K-contiguous operand: Y rows (dy values, stride ldy) may be odd-strided, so
-  // the rank-dy update runs through the in-place row kernel instead of the TMA GEMM
-  for (long s0 = 0; s0 < n; s0 += chunk_rows) {
+  GPB_CUDA_CHECK(cudaEventRecord(aux->fork, st));
+  GPB_CUDA_CHECK(cudaStreamWaitEvent(aux->side, aux->fork, 0));
+  long c = 0;
+  for (long s0 = 0; s0 < n; s0 += chunk_rows, ++c) {
     const int rows = static_cast<int>(std::min<long>(chunk_rows, n - s0));
+    const int b = static_cast<int>(c & 1);
+    double* G = gbuf[b];
+    // caller's stream: dLoss/dKfu_c = Kfu_c R + Y_c W^T into buffer b (consumed by the reduction of chunk c - 2)
+    if (c >= 2) GPB_CUDA_CHECK(cudaStreamWaitEvent(st, aux->free_[b], 0));
     const double* P;
     long ldp;
     if (kfu_cache) {
@@ -361,19 +410,26 @@ int gpb_kuf_stats_bwd(int kind, const double* X, long n, long ldx, const double*
       if (rc) return rc;
       P = panel; ldp = ldm;
     }
-    int rc = gpb_gemm(GEMM_NN, rows, m, m, 1.0, P, ldp, R, ldr, 0.0, G, ldm, 0, stream);            // Kfu_c R
+    int rc = gpb_gemm(GEMM_NN, rows, m, m, 1.0, P, ldp, R, ldr, 0.0, G, ldm, 0, stream);
     if (rc) return rc;
-    rc = gpb_rows_scale_add_outer(G, rows, m, ldm, nullptr, 1.0, Y + s0 * ldy, dy, ldy, W, ldw, stream);   // + Y_c W^T
+    // Y rows (dy values, stride ldy) may be odd-strided: the rank-dy update runs through the in-place row kernel
+    rc = gpb_rows_scale_add_outer(G, rows, m, ldm, nullptr, 1.0, Y + s0 * ldy, dy, ldy, W, ldw, stream);
     if (rc) return rc;
+    GPB_CUDA_CHECK(cudaEventRecord(aux->ready[b], st));
+    // side stream: reduce it against dK/d(ell, sigma2, Z) while the next chunk's product runs
+    GPB_CUDA_CHECK(cudaStreamWaitEvent(aux->side, aux->ready[b], 0));
     rc = gpb_kern_bwd(kind, X + s0 * ldx, rows, ldx, Z, m, ldz, D, ell, ell_len, sigma2, G, ldm, 0, t_ell, t_s2, t_z,
-                      kb_ws, kb_bytes, stream);
+                      kb_ws, kb_bytes, aux->side);
     if (rc) return rc;
-    kuf_accumulate_kernel<<<(ell_len + 255) / 256, 256, 0, st>>>(g_ell, t_ell, ell_len);
-    kuf_accumulate_kernel<<<1, 32, 0, st>>>(g_sigma2, t_s2, 1);
-    kuf_accumulate_kernel<<<(m * D + 255) / 256, 256, 0, st>>>(gZ, t_z, static_cast<long>(m) * D);
+    kuf_accumulate_kernel<<<(ell_len + 255) / 256, 256, 0, aux->side>>>(g_ell, t_ell, ell_len);
+    kuf_accumulate_kernel<<<1, 32, 0, aux->side>>>(g_sigma2, t_s2, 1);
+    kuf_accumulate_kernel<<<(m * D + 255) / 256, 256, 0, aux->side>>>(gZ, t_z, static_cast<long>(m) * D);
     count_launch(3);
     GPB_CUDA_CHECK(cudaGetLastError());
+    GPB_CUDA_CHECK(cudaEventRecord(aux->free_[b], aux->side));
   }
+  GPB_CUDA_CHECK(cudaEventRecord(aux->join, aux->side));
+  GPB_CUDA_CHECK(cudaStreamWaitEvent(st, aux->join, 0));
   return GPB_OK;
 }
 

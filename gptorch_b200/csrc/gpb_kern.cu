@@ -136,47 +136,55 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
 
   const double sig2 = linear ? 1.0 : *p.sigma2;
   const double noise = (p.symmetric && p.noise) ? *p.noise : 0.0;
+  // Two fragment rows (16 elements) per basic block: the fp64 chains (distance, exp polynomial) of different elements are
+  // independent, and only when they sit in the same branch-free block does the scheduler interleave them.  The row bound
+  // is applied at the stores, not as a branch around the arithmetic.
 #pragma unroll
-  for (int i = 0; i < KF_MI; ++i) {
-    const int lr = wm * 32 + 8 * i + r;
-    const int row = m0 + lr;
-    if (row >= p.n1) continue;
-    const double nrow = na[lr];
-    double* krow = p.K + static_cast<long>(row) * p.ldk;
-    // All 8 values of this row first, in one branch-free block: the fp64 chains (distance, exp polynomial) of different
-    // elements are independent, and only when they sit in the same basic block does the scheduler interleave them --
-    // with a store (and its bounds branch) after every pair the kernel ran one latency-bound chain at a time.
-    double v[KF_NI][2];
+  for (int ip = 0; ip < KF_MI; ip += 2) {
+    double v[2][KF_NI][2];
 #pragma unroll
-    for (int j = 0; j < KF_NI; ++j) {
-      const int lc = wn * 32 + 8 * j + 2 * kk;
-      const int col = n0 + lc;
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = ip + ii;
+      const int lr = wm * 32 + 8 * i + r;
+      const int row = m0 + lr;
+      const double nrow = na[lr];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const double dot = acc[i][j][e];
-        const bool diag = p.symmetric && row == col + e;
-        double val;
-        if (linear) {
-          val = dot;
-        } else {
-          double r2 = (nrow + nbv[lc + e]) - 2.0 * dot;  // gptorch/util.py:84
-          r2 = fmax(r2, 0.0);                             // value of r2 - clamp(r2, max=0) (gptorch/util.py:88)
-          // K(X) diagonal: the reference's expansion leaves O(1e-16) round-off here, which sqrt() turns into
-          // O(1e-8) noise for Exp/Matern; the distance of a point to itself is exactly 0.
-          r2 = diag ? 0.0 : r2;
-          val = sig2 * kern_base(KIND, r2);
+      for (int j = 0; j < KF_NI; ++j) {
+        const int lc = wn * 32 + 8 * j + 2 * kk;
+        const int col = n0 + lc;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double dot = acc[i][j][e];
+          const bool diag = p.symmetric && row == col + e;
+          double val;
+          if (linear) {
+            val = dot;
+          } else {
+            double r2 = (nrow + nbv[lc + e]) - 2.0 * dot;  // gptorch/util.py:84
+            r2 = fmax(r2, 0.0);                             // value of r2 - clamp(r2, max=0) (gptorch/util.py:88)
+            // K(X) diagonal: the reference's expansion leaves O(1e-16) round-off here, which sqrt() turns into
+            // O(1e-8) noise for Exp/Matern; the distance of a point to itself is exactly 0.
+            r2 = diag ? 0.0 : r2;
+            val = sig2 * kern_base(KIND, r2);
+          }
+          v[ii][j][e] = diag ? val + noise : val;
         }
-        v[j][e] = diag ? val + noise : val;
       }
     }
 #pragma unroll
-    for (int j = 0; j < KF_NI; ++j) {
-      const int col = n0 + wn * 32 + 8 * j + 2 * kk;
-      if (col + 1 < p.n2 && ((p.ldk & 1) == 0)) {
-        __stcs(reinterpret_cast<double2*>(krow + col), make_double2(v[j][0], v[j][1]));
-      } else {
-        if (col < p.n2) krow[col] = v[j][0];
-        if (col + 1 < p.n2) krow[col + 1] = v[j][1];
+    for (int ii = 0; ii < 2; ++ii) {
+      const int row = m0 + wm * 32 + 8 * (ip + ii) + r;
+      if (row >= p.n1) continue;
+      double* krow = p.K + static_cast<long>(row) * p.ldk;
+#pragma unroll
+      for (int j = 0; j < KF_NI; ++j) {
+        const int col = n0 + wn * 32 + 8 * j + 2 * kk;
+        if (col + 1 < p.n2 && ((p.ldk & 1) == 0)) {
+          __stcs(reinterpret_cast<double2*>(krow + col), make_double2(v[ii][j][0], v[ii][j][1]));
+        } else {
+          if (col < p.n2) krow[col] = v[ii][j][0];
+          if (col + 1 < p.n2) krow[col + 1] = v[ii][j][1];
+        }
       }
     }
   }
