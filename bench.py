@@ -110,13 +110,32 @@ def _reference_modules():
     return rk, rl, RefGPR
 
 
+class _PortModel:
+    """Stand-in used ONLY when baseline/_ref is absent on the box: the oracle port of the same path (oracle/gp_oracle.py,
+    torch CPU fp64).  The line then says kind = "port"."""
+
+    def __init__(self, n):
+        from oracle import gp_oracle as O
+        self.O = O
+        self.X, self.Y, _ = O.synth_regression(n, D_IN)
+
+    def eval(self):
+        t0 = time.perf_counter()
+        loss, _ = self.O.gpr_loss_and_grads("Rbf", self.X, self.Y, np.ones(D_IN), 1.0, 0.01)
+        return time.perf_counter() - t0, float(loss.item())
+
+
 def _reference_model(n, mods):
+    if mods is None:
+        return _PortModel(n)
     rk, rl, RefGPR = mods
     X, Y, _ = synth_regression(n, D_IN)
     return RefGPR(X.numpy(), Y.numpy(), rk.Rbf(D_IN, ARD=True), likelihood=rl.Gaussian(variance=0.01))
 
 
 def _reference_eval(model, cuda=False):
+    if isinstance(model, _PortModel):
+        return model.eval()
     for p in model.parameters():
         p.grad = None
     if cuda:
@@ -127,6 +146,16 @@ def _reference_eval(model, cuda=False):
     if cuda:
         torch.cuda.synchronize()
     return time.perf_counter() - t0, float(loss.item())
+
+
+def _cpu_reference_modules():
+    """(modules or None, kind, description): the unmodified reference when baseline/_ref travelled with the repo, else the
+    oracle port."""
+    try:
+        return _reference_modules(), "reference", "unmodified cics-nd/gptorch (baseline/_ref, torch CPU fp64 / MKL"
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("bench.py: baseline/_ref unavailable (%r) -- timing the oracle port instead\n" % (e,))
+        return None, "port", "oracle/gp_oracle.py port of the reference path (baseline/_ref absent; torch CPU fp64 / MKL"
 
 
 def choose_cpu_sample(n_full, evals, budget_s, mods):
@@ -158,7 +187,7 @@ def extrapolate(sec, sample_n, n_full):
 
 def cpu_baseline(n_full, sample_n=0):
     """`cpu_baseline` of our arm's line: ONE evaluation of the unmodified reference on a bounded sample."""
-    mods = _reference_modules()
+    mods, kind, what = _cpu_reference_modules()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample_n = min(sample_n or choose_cpu_sample(n_full, 1, 30.0, mods), n_full)
@@ -166,8 +195,8 @@ def cpu_baseline(n_full, sample_n=0):
     sec, loss = _reference_eval(_reference_model(sample_n, mods))
     full, scale = extrapolate(sec, sample_n, n_full)
     pin = reference_pin(n_full)
-    out = {"value": 1.0 / full, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "reference",
-           "sample": "unmodified cics-nd/gptorch (baseline/_ref, torch CPU fp64 / MKL, %d threads) loss+grad at N=%d, D=%d: "
+    out = {"value": 1.0 / full, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": kind,
+           "sample": what + ", %d threads) loss+grad at N=%d, D=%d: "
                      "%.2f s measured; scaled by %.1fx to N=%d (the full-size / sample-size time ratio of the reference measured "
                      "on this pool's host where available, else (N/%d)^%.2f)" % (
                          torch.get_num_threads(), sample_n, D_IN, sec, scale, n_full, sample_n, CPU_SCALING_EXPONENT),
@@ -185,7 +214,7 @@ def run_reference(args, rank, world):
     one loss+grad evaluation at the bounded sample size."""
     if rank != 0:
         return
-    mods = _reference_modules()
+    mods, kind, what = _cpu_reference_modules()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     evals = args.steps + max(args.warmup, 1)
@@ -200,7 +229,7 @@ def run_reference(args, rank, world):
     full, scale = extrapolate(sec, sample_n, args.n)
     value = 1.0 / full
     pin = reference_pin(args.n)
-    sample = ("unmodified cics-nd/gptorch from baseline/_ref (torch CPU fp64 / MKL, %d threads): model.loss() + backward() "
+    sample = (what + ", %d threads): model.loss() + backward() "
               "at N=%d timed %.2f s/step; value scaled by %.1fx to N=%d (the full-size / sample-size time ratio of the "
               "reference measured on this pool's host where available, else (N/%d)^%.2f)" % (
                   torch.get_num_threads(), sample_n, sec, scale, args.n, sample_n, CPU_SCALING_EXPONENT))
@@ -213,7 +242,7 @@ def run_reference(args, rank, world):
         "config": workload_config(args.n, args.gpus),
         "same_config": False, "same_config_note": "the workload is the named one; each step is a bounded sample of it at "
                                                   "N=%d and `value` is an extrapolation" % sample_n,
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "reference",
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample, "sample_n": sample_n, "sample_seconds": sec, "sample_loss": loss},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
