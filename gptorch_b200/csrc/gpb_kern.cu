@@ -190,6 +190,133 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
   }
 }
 
+// D <= 16: the whole feature range is ONE staging chunk, so the distance tile can be produced in two halves of 16 fragment
+// rows -- 16 instead of 32 live accumulators per thread, which brings the kernel under 85 registers and THREE CTAs (24
+// warps) per SM: this kernel is bound by the latency of the per-element exp chains (ncu: one eligible warp per scheduler
+// 47 % of the cycles at 16 warps per SM), not by HBM or by the FP64 pipe.
+template <int KIND>
+__global__ void __launch_bounds__(KF_THREADS, 3) kern_fwd_d16_kernel(const KfwdParams p) {
+  __shared__ double As[KF_TM * KF_LD];
+  __shared__ double Bs[KF_TN * KF_LD];
+  __shared__ double na[KF_TM], nbv[KF_TN];
+  __shared__ double scale[KF_DC];
+  int tm, tn;
+  {
+    const int t = blockIdx.x;
+    if (p.lower) {
+      int q = static_cast<int>((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
+      while ((q + 1) * (q + 2) <= t) ++q;
+      while (q * (q + 1) > t) --q;
+      const int rem = t - q * (q + 1);
+      tm = 2 * q + rem / (q + 1);
+      tn = rem % (q + 1);
+    } else {
+      tm = t / p.tiles_n;
+      tn = t - tm * p.tiles_n;
+    }
+  }
+  const int m0 = tm * KF_TM, n0 = tn * KF_TN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp & 1, wn = warp >> 1;
+  const int r = lane >> 2, kk = lane & 3;
+  constexpr bool linear = KIND == KERN_LINEAR;
+
+  if (tid < KF_DC) {
+    double s = 1.0;
+    if (tid < p.D) s = p.ell[p.ell_len == 1 ? 0 : tid];
+    scale[tid] = linear ? s : 1.0 / s;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (KF_TM + KF_TN) * KF_DC; idx += KF_THREADS) {
+    const int row = idx >> 4, k = idx & 15;
+    double v = 0.0;
+    if (row < KF_TM) {
+      if (k < p.D && m0 + row < p.n1) v = p.X[static_cast<long>(m0 + row) * p.ldx + k] * scale[k];
+      As[row * KF_LD + k] = v;
+    } else {
+      const int rb = row - KF_TM;
+      if (k < p.D && n0 + rb < p.n2) {
+        const double x = p.X2[static_cast<long>(n0 + rb) * p.ldx2 + k];
+        v = linear ? x : x * scale[k];
+      }
+      Bs[rb * KF_LD + k] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < KF_TM + KF_TN) {
+    const double* src = tid < KF_TM ? &As[tid * KF_LD] : &Bs[(tid - KF_TM) * KF_LD];
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < KF_DC; ++k) s += src[k] * src[k];
+    if (tid < KF_TM) na[tid] = s;
+    else nbv[tid - KF_TM] = s;
+  }
+  __syncthreads();
+
+  const double sig2 = linear ? 1.0 : *p.sigma2;
+  const double noise = (p.symmetric && p.noise) ? *p.noise : 0.0;
+  const int ksteps = min(KF_DC, p.D + 3) / 4;
+#pragma unroll 1
+  for (int ih = 0; ih < 2; ++ih) {
+    double acc[2][KF_NI][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < KF_NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      double a[2], b[KF_NI];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = As[(wm * 32 + 8 * (2 * ih + i) + r) * KF_LD + ks * 4 + kk];
+#pragma unroll
+      for (int j = 0; j < KF_NI; ++j) b[j] = Bs[(wn * 32 + 8 * j + r) * KF_LD + ks * 4 + kk];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < KF_NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int lr = wm * 32 + 8 * (2 * ih + i) + r;
+      const int row = m0 + lr;
+      const double nrow = na[lr];
+      double v[KF_NI][2];
+#pragma unroll
+      for (int j = 0; j < KF_NI; ++j) {
+        const int lc = wn * 32 + 8 * j + 2 * kk;
+        const int col = n0 + lc;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double dot = acc[i][j][e];
+          const bool diag = p.symmetric && row == col + e;
+          double val;
+          if (linear) {
+            val = dot;
+          } else {
+            double r2 = (nrow + nbv[lc + e]) - 2.0 * dot;  // gptorch/util.py:84
+            r2 = fmax(r2, 0.0);                             // gptorch/util.py:88
+            r2 = diag ? 0.0 : r2;                           // exact zero self-distance (see kern_fwd_kernel)
+            val = sig2 * kern_base(KIND, r2);
+          }
+          v[j][e] = diag ? val + noise : val;
+        }
+      }
+      if (row < p.n1) {
+        double* krow = p.K + static_cast<long>(row) * p.ldk;
+#pragma unroll
+        for (int j = 0; j < KF_NI; ++j) {
+          const int col = n0 + wn * 32 + 8 * j + 2 * kk;
+          if (col + 1 < p.n2 && ((p.ldk & 1) == 0)) {
+            __stcs(reinterpret_cast<double2*>(krow + col), make_double2(v[j][0], v[j][1]));
+          } else {
+            if (col < p.n2) krow[col] = v[j][0];
+            if (col + 1 < p.n2) krow[col + 1] = v[j][1];
+          }
+        }
+      }
+    }
+  }
+}
+
 int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int n2, long ldx2, int D,
              const double* ell, int ell_len, const double* sigma2, const double* noise, int fill, double* K,
              long ldk, cudaStream_t stream) {
@@ -217,6 +344,19 @@ int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int 
   if (p.lower) {
     const int q = tiles_m / 2;               // complete pairs of tile rows
     ntiles = q * (q + 1) + ((tiles_m & 1) ? (q + 1) : 0);
+  }
+  if (D <= KF_DC) {
+    switch (kind) {
+      case KERN_RBF: kern_fwd_d16_kernel<KERN_RBF><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+      case KERN_EXP: kern_fwd_d16_kernel<KERN_EXP><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+      case KERN_MATERN32: kern_fwd_d16_kernel<KERN_MATERN32><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+      case KERN_MATERN52: kern_fwd_d16_kernel<KERN_MATERN52><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+      case KERN_LINEAR: kern_fwd_d16_kernel<KERN_LINEAR><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+      default: kern_fwd_d16_kernel<KERN_PERIODIC><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+    }
+    count_launch();
+    GPB_CUDA_CHECK(cudaGetLastError());
+    return GPB_OK;
   }
   switch (kind) {
     case KERN_RBF: kern_fwd_kernel<KERN_RBF><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
