@@ -154,6 +154,9 @@ diag_block_kernel(double* __restrict__ A0, long lda, int n, double* __restrict__
           const double bf = Ib[(b * DG_SB + 8 * jn + r8) * DG_ILD + 4 * ks + kk];
           dmma884(acc[jn][0], acc[jn][1], af[ks], bf);
         }
+      // the strip is rewritten in place by the lanes of this warp: every lane's operand loads precede the warp-collective
+      // DMMA, the barrier makes that ordering explicit (compute-sanitizer racecheck: WAR between lanes otherwise)
+      __syncwarp();
 #pragma unroll
       for (int jn = 0; jn < 2; ++jn) {
         S[row * DG_LD + o + 8 * jn + 2 * kk] = acc[jn][0];
