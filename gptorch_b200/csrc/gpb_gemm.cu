@@ -36,6 +36,11 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 using CfgL = GemmCfg<128, 128, 64, 32, 5>;
+// H: the 128 x 128 tile split into a left and a right 128 x 64 half, one CTA each (4 consumer warps with the same 64 x 32
+// warp tiles, 4 stages of 24 KB): TWO CTAs per SM, so that the epilogue (C read-modify-write), the launch gap and the
+// pipeline fill of one overlap the main loop of the other instead of idling the FP64 pipe.  Tiles are enumerated in 128 x 128
+// units exactly as for L (same super-block order); blockIdx.x & 1 selects the half.
+using CfgH = GemmCfg<128, 64, 64, 32, 4>;
 using CfgS = GemmCfg<64, 64, 32, 32, 6>;
 // T: row strips for the in-place right-TRSM base case (N <= 128 = BN: one CTA owns all columns of its rows, so
 // every TMA read of those rows completes before the CTA's own epilogue overwrites them).
@@ -52,6 +57,8 @@ struct GemmKParams {
   unsigned flags;
   int tiles_m, tiles_n;
   unsigned zero;   // always 0 at run time; opaque to the compiler (see the stage-release dependency in the main loop)
+  long long stagger;            // CfgH: start delay (clocks) of the CTAs with stagger_lo <= blockIdx.x < stagger_hi
+  unsigned stagger_lo, stagger_hi;
 };
 
 // Swizzled byte offset inside a "row-tile" (rows of 16 doubles = 128 B, SWIZZLE_128B): element (row, col).
@@ -60,7 +67,7 @@ __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t col) {
 }
 
 template <int MODE, class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::BM == 128 && Cfg::BN == 64) ? 2 : 1)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const GemmKParams p) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, MI = Cfg::MI, NI = Cfg::NI;
@@ -77,10 +84,11 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   // Tiles are visited in super-blocks of SUPER x SUPER tiles (about one wave of 148 CTAs): the CTAs that are
   // resident together then share SUPER row panels and SUPER column panels, which stay in L2 instead of being
   // re-fetched from HBM for every tile.  Super-block rows ascend, so LAUUM's heaviest tiles still go first.
+  constexpr bool HALF = (BM == 128 && BN == 64);
   int tm, tn;
   {
     constexpr int SUPER = 12;
-    int t = blockIdx.x;
+    int t = HALF ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     if (p.flags & GF_LOWER_TILES) {
       const int T = p.tiles_m;
       int sm = 0, r0 = 0, h = min(SUPER, T);
@@ -121,8 +129,15 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       tn = c0 + q % w;
     }
   }
-  const int m0 = tm * BM, n0 = tn * BN;
+  const int m0 = tm * BM, n0 = HALF ? tn * 128 + static_cast<int>(blockIdx.x & 1) * 64 : tn * BN;
   const int bz = blockIdx.y;
+  if (HALF && n0 >= p.N) return;     // right half of a ragged last tile column
+  if (HALF && p.stagger > 0 && blockIdx.x >= p.stagger_lo && blockIdx.x < p.stagger_hi) {
+    // first wave only: the CTAs that land in the second slot of each SM start half a tile late, so that the two
+    // co-resident CTAs of an SM alternate between main loop and epilogue instead of idling the pipe together
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.stagger) { __nanosleep(200); }
+  }
 
   int k_lo = 0, k_hi = p.K;
   if (p.flags & GF_KLO_M) k_lo = max(k_lo, m0);
@@ -387,14 +402,45 @@ static int launch_cfg(const CUtensorMap& mapA, const CUtensorMap& mapB, GemmKPar
                       cudaStream_t stream) {
   static std::atomic<int> smem_state[GPB_MAX_DEVICES];
   if (int rc = ensure_dynamic_smem(gemm_dmma_kernel<MODE, Cfg>, Cfg::SMEM_BYTES, smem_state)) return rc;
+  constexpr bool HALF = (Cfg::BM == 128 && Cfg::BN == 64);
   kp.tiles_m = (a.M + Cfg::BM - 1) / Cfg::BM;
-  kp.tiles_n = (a.N + Cfg::BN - 1) / Cfg::BN;
+  kp.tiles_n = HALF ? (a.N + 127) / 128 : (a.N + Cfg::BN - 1) / Cfg::BN;
   int ntiles;
   if (a.flags & GF_LOWER_TILES) {
     if (kp.tiles_m != kp.tiles_n) return GPB_ERR_BADARG;
     ntiles = kp.tiles_m * (kp.tiles_m + 1) / 2;
   } else {
     ntiles = kp.tiles_m * kp.tiles_n;
+  }
+  if (HALF) {
+    ntiles *= 2;
+    static std::atomic<int> carve_state[GPB_MAX_DEVICES];
+    {
+      int d0 = 0;
+      cudaGetDevice(&d0);
+      if (d0 >= 0 && d0 < GPB_MAX_DEVICES && carve_state[d0].load(std::memory_order_relaxed) == 0) {
+        // two CTAs of ~100 KB each: ask for the largest shared-memory carve-out
+        cudaFuncSetAttribute(gemm_dmma_kernel<MODE, Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        carve_state[d0].store(1, std::memory_order_relaxed);
+      }
+    }
+    static const long stagger_env = []() { const char* v = getenv("GPB_GEMM_STAGGER"); return v && *v ? atol(v) : -1L; }();
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static int sm_count[GPB_MAX_DEVICES] = {0};
+    if (dev >= 0 && dev < GPB_MAX_DEVICES) {
+      if (sm_count[dev] == 0) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+      sms = sm_count[dev];
+    }
+    // half a tile of FP64-pipe time when two CTAs share the pipe: 128 x 64 x K FMA at 64 FMA/clk/SM
+    const long long half_tile = static_cast<long long>(a.K) * 128 * 64 / 64 / 2;
+    // measured: the two CTAs of an SM fall out of phase on their own (stagger 0 = auto = 35.9 TFLOP/s); the explicit
+    // first-wave delay stays available through GPB_GEMM_STAGGER=<clocks> for experiments
+    (void)half_tile;
+    kp.stagger = stagger_env > 0 ? stagger_env : 0;
+    kp.stagger_lo = static_cast<unsigned>(sms);
+    kp.stagger_hi = static_cast<unsigned>(2 * sms);
   }
   dim3 grid(ntiles, a.batch, 1);
   gemm_dmma_kernel<MODE, Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, kp);
@@ -425,6 +471,12 @@ static int launch_mode(const CUtensorMap& mapA, const CUtensorMap& mapB, const G
   // (VFE forward statistics 52.2 -> 50.0 ms per 1.25e6-row shard)
   const long tiles_rule = (a.flags & GF_LOWER_TILES) && a.batch > 1 ? tiles / a.batch : tiles;
   if (tiles_rule <= small) return launch_cfg<MODE, CfgS>(mapA, mapB, kp, a, stream);
+  // From about two waves of 128 x 128 tiles on, the half-tile configuration (two CTAs per SM) wins: measured SYRK
+  // m = 28672, k = 2048: 35.19 -> 35.88 TFLOP/s, m = 8192: 33.15 -> 34.54; NN 131072 x 1024 x 1024: 34.94 -> 35.69
+  // (tools/bench_gemm_half.py).  GPB_GEMM_HALF=<min tiles> overrides the threshold, a huge value disables it (tuning aid).
+  static const long half_env = []() { const char* v = getenv("GPB_GEMM_HALF"); return v && *v ? atol(v) : 0L; }();
+  const long half_min = half_env > 0 ? half_env : GEMM_HALF_TILE_THRESHOLD;
+  if (tiles >= half_min) return launch_cfg<MODE, CfgH>(mapA, mapB, kp, a, stream);
   return launch_cfg<MODE, CfgL>(mapA, mapB, kp, a, stream);
 }
 
@@ -443,6 +495,7 @@ int gemm_launch(GemmMode mode, const CUtensorMap& mapA, const CUtensorMap& mapB,
   kp.flags = a.flags;
   kp.tiles_m = kp.tiles_n = 0;
   kp.zero = 0u;
+  kp.stagger = 0; kp.stagger_lo = kp.stagger_hi = 0u;
   if ((a.flags & GF_DIAG_TO_WS) && (a.Cdiag == nullptr || (a.ldd & 1))) return GPB_ERR_BADARG;
   switch (mode) {
     case GEMM_NT: return launch_mode<GEMM_NT>(mapA, mapB, kp, a, stream);

@@ -40,6 +40,7 @@ struct GemmArgs {
 // tiles run with 64x64 tiles instead (4x the CTAs).
 constexpr int GEMM_SMALL_TILE_THRESHOLD = 64;
 constexpr int GEMM_SMALL_TILE_THRESHOLD_LOWER = 300;
+constexpr int GEMM_HALF_TILE_THRESHOLD = 300;   // from this many 128x128 tiles on: 128x64 half tiles, two CTAs per SM
 int gemm_launch(GemmMode mode, const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmArgs& args,
                 cudaStream_t stream);
 
