@@ -98,6 +98,48 @@ def test_gemm_modes(shape):
         assert rel_err(nv.gemm(mode, a.cuda(), b.cuda()).cpu().numpy(), (A @ B.t()).numpy()) < 1e-13
 
 
+@pytest.mark.parametrize("shape", [(2600, 2500, 300), (3072, 1704, 130), (2560, 2630, 64)])
+def test_gemm_half_tile_configuration(shape):
+    """Launches of >= 300 tiles run the 128 x 64 half-tile configuration (two CTAs per SM): all three operand layouts,
+    ragged edges on both sides of a half boundary (N mod 128 below and above 64), accumulate, vs float64 matmul on the CPU."""
+    from gptorch_b200 import _native as nv
+    m, n, k = shape
+    assert ((m + 127) // 128) * ((n + 127) // 128) >= 300
+    g = torch.Generator().manual_seed(21)
+    A = torch.randn(m, k, generator=g, dtype=torch.float64)
+    B = torch.randn(n, k, generator=g, dtype=torch.float64)
+    C0 = torch.randn(m, n, generator=g, dtype=torch.float64)
+    ref = 0.5 * C0 - A @ B.t()
+    for mode, a, b in ((nv.GEMM_NT, A, B), (nv.GEMM_TN, A.t().contiguous(), B.t().contiguous()), (nv.GEMM_NN, A, B.t().contiguous())):
+        buf, ld = nv._aligned_empty(m, n, torch.device("cuda"))
+        C = buf[:, :n]
+        C.copy_(C0)
+        nv.gemm(mode, a.cuda(), b.cuda(), alpha=-1.0, beta=0.5, C=C)
+        assert rel_err(C.cpu().numpy(), ref.numpy()) < 1e-13
+
+
+def test_gemm_half_tile_lower_and_triangular_k_ranges():
+    """The same configuration for the SYRK / LAUUM shapes: lower tiles only, and the k-range flags of triangular operands."""
+    from gptorch_b200 import _native as nv
+    n, k = 3400, 500                      # 27 x 28 / 2 = 378 lower tiles
+    g = torch.Generator().manual_seed(22)
+    A = torch.randn(n, k, generator=g, dtype=torch.float64)
+    C0 = torch.randn(n, n, generator=g, dtype=torch.float64)
+    C = nv._aligned_empty(n, n, torch.device("cuda"))[0][:, :n]
+    C.copy_(C0)
+    nv.gemm(nv.GEMM_NT, A.cuda(), A.cuda(), alpha=-1.0, beta=1.0, C=C, lower_only=True)
+    ref = C0 - A @ A.t()
+    assert rel_err(torch.tril(C).cpu().numpy(), torch.tril(ref).numpy()) < 1e-13
+    # T T^T with T upper triangular (k >= row and k >= column): the LAUUM product of the blocked inverse
+    T = torch.triu(torch.randn(n, n, generator=g, dtype=torch.float64))
+    out = nv.gemm(nv.GEMM_NT, T.cuda(), T.cuda(), lower_only=True, flags=nv.GF_KLO_M | nv.GF_KLO_N)
+    assert rel_err(torch.tril(out).cpu().numpy(), torch.tril(T @ T.t()).numpy()) < 1e-12
+    # X T with T upper triangular (k <= column)
+    X = torch.randn(2700, n, generator=g, dtype=torch.float64)
+    out = nv.gemm(nv.GEMM_NN, X.cuda(), T.cuda(), flags=nv.GF_KHI_N)
+    assert rel_err(out.cpu().numpy(), (X @ T).numpy()) < 1e-12
+
+
 def test_gemm_is_race_free_under_repetition():
     """Regression test for the stage-release race (an LDS of a ring stage still in flight when the TMA producer was
     allowed to overwrite it): many repetitions of a ragged, long-k accumulate must stay exact."""
