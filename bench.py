@@ -346,7 +346,7 @@ def fp64_peak_live():
 
 
 PROBE_M, PROBE_K = 16384, 2048
-PROBE_TRAFFIC_BYTES = 5.50e9   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_syrk_16384x2048.txt
+PROBE_TRAFFIC_BYTES = 5.066e9   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_ncu_syrk_16384x2048_half_tile.txt
 
 
 def dominant_launch_probe():
@@ -510,7 +510,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "achieved": o3_tflops, "peak": peak_issue, "unit": "TFLOP/s",
                      "frac": (o3_tflops / peak_issue) if o3_tflops else None,
                      "traffic": PROBE_TRAFFIC_BYTES,
-                     "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4 fed by TMA) -- > 95 % of gpb_potrf_lower + gpb_potri_lower",
+                     "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4 fed by TMA; 128x64 half tiles, two CTAs per SM) -- > 95 % of "
+                               "gpb_potrf_lower + gpb_potri_lower",
                      "algorithmic": "achieved = N^3 flop per eval (potrf N^3/3 + potri 2N^3/3) / CUDA-event time of those two "
                                     "phases inside the timed steps (all their launches, including the latency-bound ones)",
                      "peak_source": "measured live: FP64 tensor-pipe issue ceiling (gpb_dmma_issue_probe: independent "
@@ -521,7 +522,8 @@ def run_ours(args, rank, world, local_rank):
                      "chol_frac": (chol_tflops / peak_issue) if chol_tflops else None,
                      "launch_probe": probe,
                      "traffic_note": "dram__bytes_read+write of ONE launch of the probe shape from ncu --set full "
-                                     "(profiles/r01_ncu_syrk_16384x2048.txt); algorithmic bytes of that launch: 2.43e9"},
+                                     "(profiles/r02_ncu_syrk_16384x2048_half_tile.txt: DMMA sub-pipe 96.5 % active); "
+                                     "algorithmic bytes of that launch: 2.43e9"},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
