@@ -13,6 +13,7 @@
 #include "gpb_kernfn.cuh"
 #include "gpb_kernbwd.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace gpb {
 
@@ -25,6 +26,7 @@ constexpr int KF_MI = 4, KF_NI = 4;   // 8x8 DMMA fragments per warp tile (32 x 
 constexpr int KF_DC = 16;    // feature chunk staged per pass
 constexpr int KF_LD = 20;    // padded row stride (doubles): 20 mod 16 == 4 -> conflict-free DMMA fragment loads
 constexpr int KF_THREADS = 256;
+constexpr long KF_SQUARE_MIN_TILES = 4096;   // ~9 waves of 148 x 3 CTAs
 
 struct KfwdParams {
   int kind;
@@ -190,21 +192,32 @@ __global__ void __launch_bounds__(KF_THREADS, 2) kern_fwd_kernel(const KfwdParam
   }
 }
 
-// D <= 16: the whole feature range is ONE staging chunk, so the distance tile can be produced in two halves of 16 fragment
+// D <= 16: the whole feature range is ONE staging chunk, so the distance tile can be produced in passes of 16 fragment
 // rows -- 16 instead of 32 live accumulators per thread, which brings the kernel under 85 registers and THREE CTAs (24
-// warps) per SM: this kernel is bound by the latency of the per-element exp chains (ncu: one eligible warp per scheduler
-// 47 % of the cycles at 16 warps per SM), not by HBM or by the FP64 pipe.
-template <int KIND>
+// warps) per SM.  Round-2 ncu (profiles/r02_ncu_covariance_kernels_n32768.txt): 47 % of the stall samples of the first
+// version sat in the staging prologue (a load -> scale -> store loop of 12 dependent global-memory round trips per CTA,
+// plus spills in the epilogue), not in the exp chains; the one-thread-per-row staging below exposes ONE round trip, and
+// four-element batches (kern_base_vec) keep the epilogue free of spills: 1.80 -> 1.34 ms at N = 32768, D = 8 (RBF).
+template <int KIND, int HALVES>
 __global__ void __launch_bounds__(KF_THREADS, 3) kern_fwd_d16_kernel(const KfwdParams p) {
-  __shared__ double As[KF_TM * KF_LD];
-  __shared__ double Bs[KF_TN * KF_LD];
-  __shared__ double na[KF_TM], nbv[KF_TN];
+  constexpr int RP = 2;                // fragment rows per pass
+  constexpr int TM = KF_TM * HALVES;   // HALVES = 2: two 64-row halves share one staged X2 block (128 x 128 tile)
+  __shared__ __align__(16) double As[TM * KF_LD];
+  __shared__ __align__(16) double Bs[KF_TN * KF_LD];
+  __shared__ double na[TM], nbv[KF_TN];
   __shared__ double scale[KF_DC];
   int tm, tn;
   {
     const int t = blockIdx.x;
-    if (p.lower) {
-      int q = static_cast<int>((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
+    if (p.lower && HALVES == 2) {
+      // square tiles: plain triangular enumeration, tile row tm holds column tiles 0 .. tm
+      int q = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);   // estimate, corrected below
+      while ((q + 1) * (q + 2) / 2 <= t) ++q;
+      while (q * (q + 1) / 2 > t) --q;
+      tm = q;
+      tn = t - q * (q + 1) / 2;
+    } else if (p.lower) {
+      int q = static_cast<int>((sqrtf(4.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);   // estimate, corrected below
       while ((q + 1) * (q + 2) <= t) ++q;
       while (q * (q + 1) > t) --q;
       const int rem = t - q * (q + 1);
@@ -215,101 +228,129 @@ __global__ void __launch_bounds__(KF_THREADS, 3) kern_fwd_d16_kernel(const KfwdP
       tn = t - tm * p.tiles_n;
     }
   }
-  const int m0 = tm * KF_TM, n0 = tn * KF_TN;
+  const int m0 = tm * TM, n0 = tn * KF_TN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 1, wn = warp >> 1;
   const int r = lane >> 2, kk = lane & 3;
   constexpr bool linear = KIND == KERN_LINEAR;
 
-  if (tid < KF_DC) {
-    double s = 1.0;
-    if (tid < p.D) s = p.ell[p.ell_len == 1 ? 0 : tid];
-    scale[tid] = linear ? s : 1.0 / s;
-  }
-  __syncthreads();
-  for (int idx = tid; idx < (KF_TM + KF_TN) * KF_DC; idx += KF_THREADS) {
-    const int row = idx >> 4, k = idx & 15;
-    double v = 0.0;
-    if (row < KF_TM) {
-      if (k < p.D && m0 + row < p.n1) v = p.X[static_cast<long>(m0 + row) * p.ldx + k] * scale[k];
-      As[row * KF_LD + k] = v;
-    } else {
-      const int rb = row - KF_TM;
-      if (k < p.D && n0 + rb < p.n2) {
-        const double x = p.X2[static_cast<long>(n0 + rb) * p.ldx2 + k];
-        v = linear ? x : x * scale[k];
+  // Staging: one thread per row (64 rows of X, 128 of X2).  The row's loads are independent instructions issued BEFORE
+  // the barrier that publishes the reciprocal length scales, so a CTA exposes one global-memory latency, not one per
+  // staging iteration; scaling, the padded shared-memory row and the row's squared norm then come out of registers in
+  // the same thread (the norm is the k-ordered sum of the staged values, as before).
+  const bool is_a = tid < TM;
+  const int srow = is_a ? tid : tid - TM;
+  const double sig2 = linear ? 1.0 : __ldg(p.sigma2);   // issued with the row loads, ahead of the barriers
+  const double noise = (p.symmetric && p.noise) ? __ldg(p.noise) : 0.0;
+  double xr[KF_DC];
+  if (tid < TM + KF_TN) {
+    const bool in = is_a ? (m0 + srow < p.n1) : (n0 + srow < p.n2);
+    const double* src = is_a ? p.X + static_cast<long>(m0 + srow) * p.ldx : p.X2 + static_cast<long>(n0 + srow) * p.ldx2;
+    const bool vec = (((p.ldx | p.ldx2 | static_cast<long>(p.D)) & 1) == 0) &&
+                     (((reinterpret_cast<uintptr_t>(p.X) | reinterpret_cast<uintptr_t>(p.X2)) & 15) == 0);
+    if (vec) {
+#pragma unroll
+      for (int k = 0; k < KF_DC; k += 2) {
+        double2 v = make_double2(0.0, 0.0);
+        if (in && k < p.D) v = __ldg(reinterpret_cast<const double2*>(src + k));
+        xr[k] = v.x;
+        xr[k + 1] = v.y;
       }
-      Bs[rb * KF_LD + k] = v;
+    } else {
+#pragma unroll
+      for (int k = 0; k < KF_DC; ++k) xr[k] = (in && k < p.D) ? __ldg(src + k) : 0.0;
     }
   }
+  if (tid >= KF_THREADS - KF_DC) {
+    const int k = tid - (KF_THREADS - KF_DC);
+    double s = 1.0;
+    if (k < p.D) s = p.ell[p.ell_len == 1 ? 0 : k];
+    scale[k] = linear ? s : 1.0 / s;
+  }
   __syncthreads();
-  if (tid < KF_TM + KF_TN) {
-    const double* src = tid < KF_TM ? &As[tid * KF_LD] : &Bs[(tid - KF_TM) * KF_LD];
+  if (tid < TM + KF_TN) {
+    double* dst = is_a ? &As[srow * KF_LD] : &Bs[srow * KF_LD];
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < KF_DC; ++k) s += src[k] * src[k];
-    if (tid < KF_TM) na[tid] = s;
-    else nbv[tid - KF_TM] = s;
+    for (int k = 0; k < KF_DC; k += 2) {
+      double2 v;
+      v.x = (linear && !is_a) ? xr[k] : xr[k] * scale[k];
+      v.y = (linear && !is_a) ? xr[k + 1] : xr[k + 1] * scale[k + 1];
+      *reinterpret_cast<double2*>(dst + k) = v;
+      s += v.x * v.x;
+      s += v.y * v.y;
+    }
+    if (is_a) na[srow] = s;
+    else nbv[srow] = s;
   }
   __syncthreads();
 
-  const double sig2 = linear ? 1.0 : *p.sigma2;
-  const double noise = (p.symmetric && p.noise) ? *p.noise : 0.0;
   const int ksteps = min(KF_DC, p.D + 3) / 4;
 #pragma unroll 1
-  for (int ih = 0; ih < 2; ++ih) {
-    double acc[2][KF_NI][2];
+  for (int ihh = 0; ihh < HALVES * 4 / RP; ++ihh) {
+    const int ih = ihh % (4 / RP), h0 = (ihh / (4 / RP)) * KF_TM;
+    double acc[RP][KF_NI][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < RP; ++i)
 #pragma unroll
       for (int j = 0; j < KF_NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int ks = 0; ks < ksteps; ++ks) {
-      double a[2], b[KF_NI];
+      double a[RP], b[KF_NI];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) a[i] = As[(wm * 32 + 8 * (2 * ih + i) + r) * KF_LD + ks * 4 + kk];
+      for (int i = 0; i < RP; ++i) a[i] = As[(h0 + wm * 32 + 8 * (RP * ih + i) + r) * KF_LD + ks * 4 + kk];
 #pragma unroll
       for (int j = 0; j < KF_NI; ++j) b[j] = Bs[(wn * 32 + 8 * j + r) * KF_LD + ks * 4 + kk];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < RP; ++i)
 #pragma unroll
         for (int j = 0; j < KF_NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int lr = wm * 32 + 8 * (2 * ih + i) + r;
+    for (int i = 0; i < RP; ++i) {
+      const int lr = h0 + wm * 32 + 8 * (RP * ih + i) + r;
       const int row = m0 + lr;
       const double nrow = na[lr];
-      double v[KF_NI][2];
+      double* krow = p.K + static_cast<long>(row) * p.ldk;
+      // four elements (two column pairs) per batch: their exp chains are issued interleaved (kern_base_vec)
 #pragma unroll
-      for (int j = 0; j < KF_NI; ++j) {
-        const int lc = wn * 32 + 8 * j + 2 * kk;
-        const int col = n0 + lc;
+      for (int jp = 0; jp < KF_NI; jp += 2) {
+        double v[4];
+        bool diag[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int q = 0; q < 4; ++q) {
+          const int j = jp + (q >> 1), e = q & 1;
+          const int lc = wn * 32 + 8 * j + 2 * kk;
           const double dot = acc[i][j][e];
-          const bool diag = p.symmetric && row == col + e;
-          double val;
+          diag[q] = p.symmetric && row == n0 + lc + e;
           if (linear) {
-            val = dot;
+            v[q] = dot;
           } else {
             double r2 = (nrow + nbv[lc + e]) - 2.0 * dot;  // gptorch/util.py:84
             r2 = fmax(r2, 0.0);                             // gptorch/util.py:88
-            r2 = diag ? 0.0 : r2;                           // exact zero self-distance (see kern_fwd_kernel)
-            val = sig2 * kern_base(KIND, r2);
+            v[q] = diag[q] ? 0.0 : r2;                      // exact zero self-distance (see kern_fwd_kernel)
           }
-          v[j][e] = diag ? val + noise : val;
         }
-      }
-      if (row < p.n1) {
-        double* krow = p.K + static_cast<long>(row) * p.ldk;
+        if constexpr (KIND == KERN_RBF || KIND == KERN_EXP || KIND == KERN_MATERN32 || KIND == KERN_MATERN52) {
+          kern_base_vec<KIND, 4>(v);
+        } else if (!linear) {
 #pragma unroll
-        for (int j = 0; j < KF_NI; ++j) {
-          const int col = n0 + wn * 32 + 8 * j + 2 * kk;
-          if (col + 1 < p.n2 && ((p.ldk & 1) == 0)) {
-            __stcs(reinterpret_cast<double2*>(krow + col), make_double2(v[j][0], v[j][1]));
-          } else {
-            if (col < p.n2) krow[col] = v[j][0];
-            if (col + 1 < p.n2) krow[col + 1] = v[j][1];
+          for (int q = 0; q < 4; ++q) v[q] = kern_base(KIND, v[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!linear) v[q] = sig2 * v[q];
+          v[q] = diag[q] ? v[q] + noise : v[q];
+        }
+        if (row < p.n1) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int col = n0 + wn * 32 + 8 * (jp + jj) + 2 * kk;
+            if (col + 1 < p.n2 && ((p.ldk & 1) == 0)) {
+              __stcs(reinterpret_cast<double2*>(krow + col), make_double2(v[2 * jj], v[2 * jj + 1]));
+            } else {
+              if (col < p.n2) krow[col] = v[2 * jj];
+              if (col + 1 < p.n2) krow[col + 1] = v[2 * jj + 1];
+            }
           }
         }
       }
@@ -337,23 +378,36 @@ int kern_fwd(int kind, const double* X, int n1, long ldx, const double* X2, int 
   p.lower = (fill == 1);
   if (p.lower && !p.symmetric) return GPB_ERR_BADARG;
   p.K = K; p.ldk = ldk;
-  const int tiles_m = (n1 + KF_TM - 1) / KF_TM;
+  // D <= 16 kernel: 128 x 128 tiles (two row halves per staged X2 block) once the 64-row tiling has CTAs to spare
+  static const int force_square = [] { const char* e = getenv("GPB_KFWD_SQUARE"); return e ? atoi(e) : -1; }();
+  const long tiles64 = static_cast<long>((n1 + KF_TM - 1) / KF_TM) * ((p.n2 + KF_TN - 1) / KF_TN) / (p.lower ? 2 : 1);
+  const bool square = D <= KF_DC && (force_square >= 0 ? force_square != 0 : tiles64 >= KF_SQUARE_MIN_TILES);
+  const int tile_rows = square ? 2 * KF_TM : KF_TM;
+  const int tiles_m = (n1 + tile_rows - 1) / tile_rows;
   p.tiles_n = (p.n2 + KF_TN - 1) / KF_TN;
   // lower fill: tile row tm (64 rows) covers column tiles 0 .. tm/2 (128 columns each)
   int ntiles = tiles_m * p.tiles_n;
-  if (p.lower) {
+  if (p.lower && square) {
+    ntiles = tiles_m * (tiles_m + 1) / 2;
+  } else if (p.lower) {
     const int q = tiles_m / 2;               // complete pairs of tile rows
     ntiles = q * (q + 1) + ((tiles_m & 1) ? (q + 1) : 0);
   }
   if (D <= KF_DC) {
+#define GPB_KF16(KIND)                                                                                   \
+  do {                                                                                                   \
+    if (square) kern_fwd_d16_kernel<KIND, 2><<<ntiles, KF_THREADS, 0, stream>>>(p);                      \
+    else kern_fwd_d16_kernel<KIND, 1><<<ntiles, KF_THREADS, 0, stream>>>(p);                             \
+  } while (0)
     switch (kind) {
-      case KERN_RBF: kern_fwd_d16_kernel<KERN_RBF><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
-      case KERN_EXP: kern_fwd_d16_kernel<KERN_EXP><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
-      case KERN_MATERN32: kern_fwd_d16_kernel<KERN_MATERN32><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
-      case KERN_MATERN52: kern_fwd_d16_kernel<KERN_MATERN52><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
-      case KERN_LINEAR: kern_fwd_d16_kernel<KERN_LINEAR><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
-      default: kern_fwd_d16_kernel<KERN_PERIODIC><<<ntiles, KF_THREADS, 0, stream>>>(p); break;
+      case KERN_RBF: GPB_KF16(KERN_RBF); break;
+      case KERN_EXP: GPB_KF16(KERN_EXP); break;
+      case KERN_MATERN32: GPB_KF16(KERN_MATERN32); break;
+      case KERN_MATERN52: GPB_KF16(KERN_MATERN52); break;
+      case KERN_LINEAR: GPB_KF16(KERN_LINEAR); break;
+      default: GPB_KF16(KERN_PERIODIC); break;
     }
+#undef GPB_KF16
     count_launch();
     GPB_CUDA_CHECK(cudaGetLastError());
     return GPB_OK;

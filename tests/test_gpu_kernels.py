@@ -371,3 +371,38 @@ def test_linear_kdiag_native_forward_and_gradient():
     assert rel_err(kd.detach().cpu().numpy(), ref.detach().numpy()) < 1e-14
     assert rel_err(Xc.grad.cpu().numpy(), Xr.grad.numpy()) < 1e-13
     assert rel_err(kern.variance.grad.cpu().numpy(), raw.grad.numpy()) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["Rbf", "Matern52"])
+def test_forward_square_tile_path(name):
+    """Sizes past the point where the D <= 16 forward kernel switches to 128 x 128 tiles (gpb_kern.cu, KF_SQUARE_MIN_TILES):
+    a ragged rows x M panel (odd D: scalar row loads) and a symmetric fill, full and lower, against the oracle."""
+    from oracle import gp_oracle as O
+    from gptorch_b200 import _native as nv
+    from gptorch_b200 import kernels
+    g = torch.Generator().manual_seed(11)
+    kind = {"Rbf": 0, "Matern52": 3}[name]
+    # panel: 70001 x 999 (1094 x 8 tiles of 64 x 128 -> square path), D = 5
+    d = 5
+    ell = torch.as_tensor(0.6 + 0.1 * np.arange(d))
+    var = torch.tensor([1.7], dtype=torch.float64)
+    X, Z = torch.rand(70001, d, generator=g, dtype=torch.float64), torch.rand(999, d, generator=g, dtype=torch.float64)
+    kern = getattr(kernels, name)(d, ARD=True, length_scales=ell.numpy().copy(), variance=1.7)
+    K = kern.K(X.cuda(), Z.cuda()).detach().cpu()
+    assert K.shape == (70001, 999) and rel_err(K.numpy(), O.cov(name, X, Z, ell, var).numpy()) < 1e-13
+    # symmetric: n = 9100 (143 x 72 tiles), D = 8 (vector row loads), noise on the diagonal, full vs lower fill
+    n, d = 9100, 8
+    X = torch.rand(n, d, generator=g, dtype=torch.float64)
+    ell = torch.full((d,), 0.8, dtype=torch.float64)
+    noise = torch.tensor([0.05], dtype=torch.float64)
+    full, ld = nv._aligned_empty(n, n, torch.device("cuda"))
+    low, ld2 = nv._aligned_empty(n, n, torch.device("cuda"))
+    low.zero_()
+    nv.kern_fwd(kind, X.cuda(), None, ell.cuda(), var.cuda(), noise=noise.cuda(), out=full, ldk=ld)
+    nv.kern_fwd(kind, X.cuda(), None, ell.cuda(), var.cuda(), noise=noise.cuda(), lower=True, out=low, ldk=ld2)
+    with O.exact_diagonal():
+        ref = O.cov(name, X, None, ell, var) + noise * torch.eye(n, dtype=torch.float64)
+    assert rel_err(full.cpu().numpy(), ref.numpy()) < 1e-13
+    assert torch.equal(torch.tril(low), torch.tril(full))                       # the same values, bit for bit
+    assert torch.equal(full, full.T) and bool((full.diagonal() == 1.7 + 0.05).all())
+    assert float(torch.triu(low, 129).abs().max()) == 0.0                      # nothing beyond the diagonal tiles
