@@ -406,3 +406,15 @@ def test_forward_square_tile_path(name):
     assert torch.equal(torch.tril(low), torch.tril(full))                       # the same values, bit for bit
     assert torch.equal(full, full.T) and bool((full.diagonal() == 1.7 + 0.05).all())
     assert float(torch.triu(low, 129).abs().max()) == 0.0                      # nothing beyond the diagonal tiles
+    # the same rows from a base address that is 8 but not 16 bytes aligned (scalar row loads): bit-identical output
+    for rows in (n, 300):                                                       # square-tile and 64-row-tile paths
+        flat = torch.empty(rows * d + 1, dtype=torch.float64, device="cuda")
+        Xo = flat[1:].view(rows, d)
+        Xo.copy_(X[:rows])
+        assert Xo.data_ptr() % 16 == 8 and Xo.is_contiguous()
+        Xa = X[:rows].cuda()
+        Zc = X[:4000 if rows == n else 257].cuda()                             # 143 x 32 tiles: square path
+        Ka = nv.kern_fwd(kind, Xa, Zc, ell.cuda(), var.cuda())
+        Ko = nv.kern_fwd(kind, Xo, Zc, ell.cuda(), var.cuda())
+        Kz = nv.kern_fwd(kind, Zc, Xo, ell.cuda(), var.cuda())
+        assert torch.equal(Ka, Ko) and torch.equal(Kz, Ka.T.contiguous())
