@@ -63,6 +63,9 @@ SIGNATURES = {
                            c_size_t, c_void_p]),
     "gpb_gemm": (c_int, [c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double,
                          c_void_p, c_long, c_int, c_void_p]),
+    "gpb_gemm_ozaki_nt": (c_int, [c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double, c_void_p, c_long,
+                                  c_int, c_int, c_void_p]),
+    "gpb_ozaki_config": (c_int, [c_int]),
     "gpb_gemm_splitk": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_double,
                                 c_void_p, c_long, c_long, c_int, c_void_p]),
     "gpb_kuf_stats_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

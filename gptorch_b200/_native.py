@@ -398,6 +398,31 @@ def gemm(mode, A, B, alpha=1.0, beta=0.0, C=None, lower_only=False, flags=0):
     return C
 
 
+def gemm_ozaki_nt(A, B, slices=8, alpha=1.0, beta=0.0, C=None, lower_only=False):
+    """EXPERIMENTAL: C = alpha A B^T + beta C on the INT8 tensor path by integer slicing (gpb_gemm_ozaki_nt); raises
+    NativeLibraryError with status -5 for shapes that path does not take."""
+    A = _gemm_operand(A)
+    B = A if B is None else _gemm_operand(B)
+    m, k = A.shape
+    n = B.shape[0]
+    if B.shape[1] != k:
+        raise ValueError("gemm_ozaki_nt: inner dimensions differ")
+    if C is None:
+        buf, ldc = _aligned_empty(m, n, A.device)
+        C = buf[:, :n]
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs an existing C")
+    call("gpb_gemm_ozaki_nt", m, n, k, float(alpha), ptr(A), A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C),
+         C.stride(0), 1 if lower_only else 0, int(slices), stream_ptr())
+    return C
+
+
+def ozaki_config(slices=-1):
+    """Slices used by the blocked Cholesky / inverse for their large products (0 = FP64 DMMA engine, the default).
+    Returns the previous value; slices < 0 only queries."""
+    return query("gpb_ozaki_config", int(slices))
+
+
 def gemv_t(A, Y, out, beta=1.0):
     """out (cols x dy) = beta * out + A^T Y for a tall row panel A (rows x cols) and few right-hand sides."""
     A, Y = _c(A), _c(Y)

@@ -12,6 +12,10 @@ void set_last_error_msg(const char* msg);
 int potrf_lower(double* A, int n, long lda, double* dinv, int* info, cudaStream_t stream);
 int trsm_right_lt(const double* L, int n, long ldl, const double* dinv, double* X, int m, long ldx, cudaStream_t stream);
 int tri_diag_inverse(const double* L, int n, long ldl, double* dinv, cudaStream_t stream);
+int gemm_ozaki_nt(int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
+                  double* C, long ldc, int lower, int slices, cudaStream_t stream);
+int ozaki_slices();
+void ozaki_set_slices(int s);
 size_t potri_workspace_bytes(int n);
 int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_blocks, void* workspace,
                 size_t workspace_bytes, cudaStream_t stream);
@@ -235,6 +239,16 @@ size_t gpb_gemv_t_workspace_bytes(long rows, int cols) { return gemv_t_workspace
 int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, int dy, long ldy, double beta,
                double* out, long ldo, void* workspace, size_t workspace_bytes, void* stream) {
   return gemv_t(A, rows, cols, lda, Y, dy, ldy, beta, out, ldo, workspace, workspace_bytes, S(stream));
+}
+
+int gpb_gemm_ozaki_nt(int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
+                      double* C, long ldc, int lower, int slices, void* stream) {
+  return gemm_ozaki_nt(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower, slices, S(stream));
+}
+int gpb_ozaki_config(int slices) {
+  const int prev = ozaki_slices();
+  if (slices >= 0) ozaki_set_slices(slices);
+  return prev;
 }
 
 int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,

@@ -16,6 +16,7 @@
 //               to the strictly-lower blocks; diagonal blocks go to a side buffer because the diagonal
 //               blocks of T are still being read by other CTAs.
 #include "gpb_gemm.cuh"
+#include "gpb_ozaki.cuh"
 #include <vector>
 #include <map>
 #include <mutex>
@@ -392,8 +393,16 @@ static int get_aux(cudaStream_t caller, AuxStream** out) {
   return GPB_OK;
 }
 
+// EXPERIMENTAL (gpb_ozaki.cu, off unless GPB_OZAKI / gpb_ozaki_config sets a slice count): large trailing updates on the
+// INT8 tensor path.  Shapes that path does not take fall through to the DMMA engine.
 static int syrk_update(CholCtx& c, int r0, int m, int k0, int k) {
   // A[r0:r0+m, r0:r0+m] (lower tiles) -= P P^T with P = A[r0:r0+m, k0:k0+k]
+  if (const int oz = ozaki_slices(); oz > 0 && m >= OZ_MIN_ROWS && k >= OZ_MIN_K) {
+    const double* P = c.A + static_cast<long>(r0) * c.lda + k0;
+    const int rc = gemm_ozaki_nt(m, m, k, -1.0, P, c.lda, P, c.lda, 1.0, c.A + static_cast<long>(r0) * c.lda + r0, c.lda, 1,
+                                 oz, c.stream);
+    if (rc != GPB_ERR_UNSUPPORTED) return rc;
+  }
   GemmArgs g;
   g.M = m; g.N = m; g.K = k;
   g.alpha = -1.0; g.beta = 1.0;
@@ -473,7 +482,11 @@ static int potrf_lookahead(CholCtx& c) {
       g.ldc = c.lda;
       g.ax = c0; g.ay = c2;
       g.bx = c0; g.by = c1;
-      rc = gemm_launch(GEMM_NT, c.mapA128, c.mapA128, g, s0);
+      rc = GPB_ERR_UNSUPPORTED;
+      if (const int oz = ozaki_slices(); oz > 0 && g.M >= OZ_MIN_ROWS && g.N >= OZ_MIN_COLS && g.K >= OZ_MIN_K)
+        rc = gemm_ozaki_nt(g.M, g.N, g.K, -1.0, c.A + static_cast<long>(c2) * c.lda + c0, c.lda,
+                           c.A + static_cast<long>(c1) * c.lda + c0, c.lda, 1.0, g.C, c.lda, 0, oz, s0);
+      if (rc == GPB_ERR_UNSUPPORTED) rc = gemm_launch(GEMM_NT, c.mapA128, c.mapA128, g, s0);
       if (rc) return rc;
     }
     GPB_CUDA_CHECK(cudaEventRecord(aux->ev_update, s0));
@@ -666,7 +679,26 @@ int trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace,
       g2.dbx = 0; g2.dby = static_cast<int>(s);
       g2.flags = GF_KLO_M;
       g2.batch = batch;
-      rc = gemm_launch(GEMM_NT, mapA128, mapW128, g2, stream);
+      rc = GPB_ERR_UNSUPPORTED;
+      if (const int oz = ozaki_slices(); oz > 0 && pass == 0 && s >= OZ_TRTRI_MIN_S) {
+        // EXPERIMENTAL int8 path, per problem and per row strip of T11 (entries from the strip's first column on)
+        rc = GPB_OK;
+        for (int pb = 0; pb < batch && rc == GPB_OK; ++pb) {
+          const long o2 = off + static_cast<long>(pb) * 2 * s;
+          for (int i0 = 0; i0 < s && rc == GPB_OK; i0 += OZ_TRI_STRIP) {
+            const int rows = std::min<long>(OZ_TRI_STRIP, s - i0);
+            OzEx x;
+            x.m = rows; x.n = n2; x.k = static_cast<int>(s) - i0;
+            x.alpha = -1.0; x.beta = 0.0;
+            x.A = A + (o2 + i0) * lda + o2 + i0; x.lda = lda; x.a_tri = 1; x.a_row0 = i0; x.a_col0 = i0;
+            x.B = W + static_cast<long>(p0 + pb) * s * s + i0; x.ldb = s;
+            x.C = A + (o2 + i0) * lda + o2 + s; x.ldc = lda;
+            x.slices = oz; x.stream = stream;
+            rc = gemm_ozaki_nt_ex(x);
+          }
+        }
+      }
+      if (rc == GPB_ERR_UNSUPPORTED) rc = gemm_launch(GEMM_NT, mapA128, mapW128, g2, stream);
       if (rc) return rc;
     }
   }
@@ -683,6 +715,23 @@ int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_bl
   rc = make_tmap_f64(&mapA128, A, n, n, lda, 32);
   if (rc) return rc;
   // Kinv = T T^T: strictly-lower blocks in place, diagonal blocks to kdiag_blocks.
+  if (const int oz = ozaki_slices(); oz > 0 && n >= OZ_MIN_ROWS && (n & 15) == 0) {
+    // EXPERIMENTAL int8 path: row strip [i0, i0 + R) of T only has entries from column i0 on, so its product with the rows
+    // 0 .. i0 + R runs over k in [i0, n) -- one independent sliced product per strip, no flop on the zero triangle
+    rc = GPB_OK;
+    for (int i0 = 0; i0 < n && rc == GPB_OK; i0 += OZ_TRI_STRIP) {
+      const int rows = std::min(OZ_TRI_STRIP, n - i0);
+      OzEx x;
+      x.m = rows; x.n = i0 + rows; x.k = n - i0;
+      x.A = A + static_cast<long>(i0) * lda + i0; x.lda = lda; x.a_tri = 1; x.a_row0 = i0; x.a_col0 = i0;
+      x.B = A + i0; x.ldb = lda; x.b_tri = 1; x.b_row0 = 0; x.b_col0 = i0;
+      x.C = A + static_cast<long>(i0) * lda; x.ldc = lda;
+      x.lower = 1; x.gi0 = i0; x.Cdiag = kdiag_blocks;
+      x.slices = oz; x.stream = stream;
+      rc = gemm_ozaki_nt_ex(x);
+    }
+    if (rc != GPB_ERR_UNSUPPORTED) return rc;     // (unsupported can only come from the first strip: nothing written yet)
+  }
   GemmArgs g;
   g.M = n; g.N = n; g.K = n;
   g.alpha = 1.0; g.beta = 0.0;

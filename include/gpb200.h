@@ -211,6 +211,20 @@ int gpb_gemv_t(const double* A, long rows, int cols, long lda, const double* Y, 
 int gpb_gemm(int mode, int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb,
              double beta, double* C, long ldc, int flags, void* stream);
 
+/* EXPERIMENTAL (off by default): C = beta C + alpha A B^T (A: m x k, B: n x k, row-major) computed on the
+ * INT8 tensor path by integer slicing (Ozaki scheme): every row is cut into `slices` (2..10) signed 7-bit digits relative
+ * to its own power-of-two scale, the digit products of one weight class run as one int8 GEMM over a concatenated k
+ * (cuBLASLt, loaded with dlopen on first use), and a recombination kernel applies the scales in fp64.  8 slices match a
+ * DGEMM norm-wise on covariance-conditioned operands (profiles/r02_ozaki_probe.txt).  lower != 0 (m == n): only the
+ * 128-blocks on and below the diagonal are written.  Returns GPB_ERR_UNSUPPORTED (-5) for shapes the int8 path does not
+ * take (k % 16, m % 4, n % 4, ldc odd) or when cuBLASLt cannot be loaded; callers then use gpb_gemm.
+ * No counterpart in the reference (torch.matmul in fp64, gptorch/models/gpr.py:69-86 via torch.linalg). */
+int gpb_gemm_ozaki_nt(int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
+                      double* C, long ldc, int lower, int slices, void* stream);
+/* Number of slices the blocked Cholesky uses for its large trailing updates (0 = FP64 DMMA engine, the default; the initial
+ * value comes from the environment variable GPB_OZAKI).  slices < 0 only queries.  Returns the previous value. */
+int gpb_ozaki_config(int slices);
+
 /* Split-K form: the k range is cut into ceil(k_total / k_per_split) slices (k_per_split a multiple of 16) that run
  * as independent CTAs; slice s accumulates into C + s * c_split_stride.  Used for the Gram products of the sparse
  * models, whose M x M output has far fewer tiles than the GPU has SMs (A A^T over N >> M rows,

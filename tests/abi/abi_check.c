@@ -31,6 +31,7 @@ int main(int argc, char** argv) {
       "gpb_potri_assemble", "gpb_tri_zero_upper", "gpb_add_diag", "gpb_trsv_workspace_bytes", "gpb_trsv_lower",
       "gpb_trsm_right_lt", "gpb_logdet_sumsq", "gpb_rowdot", "gpb_gemv_n",
       "gpb_rows_scale_add_outer", "gpb_gemv_t_workspace_bytes", "gpb_gemv_t", "gpb_gemm", "gpb_gemm_splitk",
+      "gpb_gemm_ozaki_nt", "gpb_ozaki_config",
       "gpb_gpr_grad_workspace_bytes", "gpb_gpr_grad", "gpb_kuf_stats_workspace_bytes", "gpb_kuf_stats_fwd",
       "gpb_kuf_stats_bwd"};
   void* lib;
