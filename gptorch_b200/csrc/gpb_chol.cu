@@ -666,7 +666,26 @@ int trtri_upper(double* A, int n, long lda, const double* dinv, void* workspace,
       g1.dax = g1.day = g1.dbx = g1.dby = static_cast<int>(2 * s);
       g1.flags = GF_KHI_M;
       g1.batch = batch;
-      rc = gemm_launch(GEMM_TN, mapA16, mapA16, g1, stream);
+      rc = GPB_ERR_UNSUPPORTED;
+      if (const int oz = ozaki_slices(); oz > 0 && pass == 0 && s >= OZ_TRTRI_MIN_S) {
+        // EXPERIMENTAL int8 path: rows [a0, a0 + R) of P^T only involve rows 0 .. a0 + R of T22 and L21; both operands are
+        // stored with the contraction index as the row, so the split transposes them
+        rc = GPB_OK;
+        for (int pb = 0; pb < batch && rc == GPB_OK; ++pb) {
+          const long o2 = off + static_cast<long>(pb) * 2 * s;
+          for (int a0 = 0; a0 < n2 && rc == GPB_OK; a0 += OZ_TRI_STRIP) {
+            const int rows = std::min(OZ_TRI_STRIP, n2 - a0);
+            OzEx x;
+            x.m = rows; x.n = static_cast<int>(s); x.k = a0 + rows;
+            x.A = A + (o2 + s) * lda + o2 + s + a0; x.lda = lda; x.a_trans = 1; x.a_tri = 1; x.a_row0 = 0; x.a_col0 = a0;
+            x.B = A + (o2 + s) * lda + o2; x.ldb = lda; x.b_trans = 1;
+            x.C = W + static_cast<long>(p0 + pb) * s * s + static_cast<long>(a0) * s; x.ldc = s;
+            x.slices = oz; x.stream = stream;
+            rc = gemm_ozaki_nt_ex(x);
+          }
+        }
+      }
+      if (rc == GPB_ERR_UNSUPPORTED) rc = gemm_launch(GEMM_TN, mapA16, mapA16, g1, stream);
       if (rc) return rc;
       // (2) T12[s x n2] = -T11 (P^T)^T     NT, A = T11 (k >= m: GF_KLO_M), B = P^T (n2 x s)
       GemmArgs g2;

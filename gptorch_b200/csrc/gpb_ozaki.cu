@@ -200,6 +200,74 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
   }
 }
 
+// Transposed operands (stored k x m, the logical operand is its transpose): column maxima first, then 128 x 32 tiles are
+// sliced and transposed through shared memory so that the int8 rows are written in 128-byte runs.
+__global__ void __launch_bounds__(256) oz_colmax_kernel(const double* __restrict__ src, long ld, int k, int m,
+                                                        double* __restrict__ scale, int tri, int row0, int col0) {
+  __shared__ double smx[8][32];
+  __shared__ int sbad[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  double mx = 0.0;
+  int bad = 0;
+  if (col < m) {
+    for (int r = ty; r < k; r += 8) {
+      if (tri && (col0 + col) < ((row0 + r) / NB) * NB) continue;
+      const double v = fabs(src[static_cast<long>(r) * ld + col]);
+      bad |= !(v <= DBL_MAX);
+      mx = fmax(mx, v);
+    }
+  }
+  smx[ty][tx] = mx;
+  sbad[ty][tx] = bad;
+  __syncthreads();
+  if (ty == 0 && col < m) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { mx = fmax(mx, smx[w][tx]); bad |= sbad[w][tx]; }
+    int e = 0;
+    if (mx > 0.0 && !bad) e = ilogb(mx) + 2;
+    e = max(-1000, min(1000, e));
+    scale[col] = bad ? __longlong_as_double(0x7ff8000000000000LL) : ldexp(1.0, e);
+  }
+}
+
+__global__ void __launch_bounds__(256) oz_split_t_kernel(const double* __restrict__ src, long ld, int k, int m, int S,
+                                                         int8_t* __restrict__ fwd, int8_t* __restrict__ rev, long ld8,
+                                                         const double* __restrict__ scale, int tri, int row0, int col0) {
+  __shared__ __align__(4) int8_t sm[OZ_MAX_SLICES][32][132];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * 128;
+  const double sc = col < m ? scale[col] : 1.0;
+  const bool bad = !(sc == sc);
+  const double inv = bad ? 0.0 : 1.0 / sc;                      // exact: sc is a power of two
+  const double radix = static_cast<double>(1 << OZ_BITS);
+  for (int t = 0; t < 16; ++t) {
+    const int rl = ty + 8 * t, r = r0 + rl;
+    double v = 0.0;
+    if (!bad && col < m && r < k && !(tri && (col0 + col) < ((row0 + r) / NB) * NB))
+      v = src[static_cast<long>(r) * ld + col] * inv;
+    for (int s = 0; s < S; ++s) {
+      v *= radix;
+      const double q = rint(v);
+      v -= q;
+      sm[s][tx][rl] = static_cast<int8_t>(static_cast<int>(q));
+    }
+  }
+  __syncthreads();
+  const int w = threadIdx.x & 31;
+  for (int rowid = threadIdx.x >> 5; rowid < S * 32; rowid += 8) {
+    const int s = rowid >> 5, a = rowid & 31;
+    const long c = static_cast<long>(blockIdx.x) * 32 + a;
+    const int r = r0 + 4 * w;
+    if (c < m && r < k) {
+      const int32_t word = *reinterpret_cast<const int32_t*>(&sm[s][a][4 * w]);
+      if (fwd) *reinterpret_cast<int32_t*>(fwd + c * ld8 + static_cast<long>(s) * k + r) = word;
+      if (rev) *reinterpret_cast<int32_t*>(rev + c * ld8 + static_cast<long>(S - 1 - s) * k + r) = word;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // recombination: C = beta C + alpha sa_i sb_j 2^-14 sum_u P_u 2^(-7 u), four columns per thread
 // ------------------------------------------------------------------------------------------------------------------
@@ -269,7 +337,7 @@ int gemm_ozaki_nt_ex(const OzEx& x) {
   const long lda = x.lda, ldb = x.ldb, ldc = x.ldc;
   cudaStream_t stream = x.stream;
   if (m <= 0 || n <= 0) return GPB_OK;
-  if (!A || !B || !C || k <= 0 || lda < k || ldb < k || ldc < n) return GPB_ERR_BADARG;
+  if (!A || !B || !C || k <= 0 || lda < (x.a_trans ? m : k) || ldb < (x.b_trans ? n : k) || ldc < n) return GPB_ERR_BADARG;
   if (slices < 2 || slices > OZ_MAX_SLICES) return GPB_ERR_BADARG;
   // shapes the int8 library path takes (everything else stays on the DMMA engine)
   if ((k & 15) || (m & 3) || (n & 3) || (ldc & 1)) return GPB_ERR_UNSUPPORTED;
@@ -285,7 +353,8 @@ int gemm_ozaki_nt_ex(const OzEx& x) {
   if (!st.handle && g_lt.Create(&st.handle) != CUBLAS_STATUS_SUCCESS) return GPB_ERR_UNSUPPORTED;
 
   const int S = slices;
-  const bool same = (A == B && lda == ldb && m == n && x.a_tri == x.b_tri && x.a_row0 == x.b_row0 && x.a_col0 == x.b_col0);
+  const bool same = (A == B && lda == ldb && m == n && !x.a_trans && !x.b_trans && x.a_tri == x.b_tri &&
+                     x.a_row0 == x.b_row0 && x.a_col0 == x.b_col0);
   const long ld8 = static_cast<long>(S) * k;
   const int strip = OZ_STRIP;
   const long ldp = (static_cast<long>(n) + 15) & ~15L;
@@ -314,9 +383,21 @@ int gemm_ozaki_nt_ex(const OzEx& x) {
   int32_t* P = reinterpret_cast<int32_t*>(st.ws + o_p);
   void* lt_ws = st.ws + o_lt;
 
-  oz_split_kernel<<<m, 256, 0, stream>>>(A, lda, k, S, a8, same ? b8 : nullptr, ld8, sa, x.a_tri, x.a_row0, x.a_col0);
-  count_launch();
-  if (!same) {
+  if (x.a_trans) {
+    oz_colmax_kernel<<<(m + 31) / 32, 256, 0, stream>>>(A, lda, k, m, sa, x.a_tri, x.a_row0, x.a_col0);
+    oz_split_t_kernel<<<dim3((m + 31) / 32, (k + 127) / 128), 256, 0, stream>>>(A, lda, k, m, S, a8, nullptr, ld8, sa, x.a_tri,
+                                                                               x.a_row0, x.a_col0);
+    count_launch(2);
+  } else {
+    oz_split_kernel<<<m, 256, 0, stream>>>(A, lda, k, S, a8, same ? b8 : nullptr, ld8, sa, x.a_tri, x.a_row0, x.a_col0);
+    count_launch();
+  }
+  if (x.b_trans) {
+    oz_colmax_kernel<<<(n + 31) / 32, 256, 0, stream>>>(B, ldb, k, n, sb, x.b_tri, x.b_row0, x.b_col0);
+    oz_split_t_kernel<<<dim3((n + 31) / 32, (k + 127) / 128), 256, 0, stream>>>(B, ldb, k, n, S, nullptr, b8, ld8, sb, x.b_tri,
+                                                                               x.b_row0, x.b_col0);
+    count_launch(2);
+  } else if (!same) {
     oz_split_kernel<<<n, 256, 0, stream>>>(B, ldb, k, S, nullptr, b8, ld8, sb, x.b_tri, x.b_row0, x.b_col0);
     count_launch();
   }

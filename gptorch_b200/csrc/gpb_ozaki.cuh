@@ -8,8 +8,12 @@ namespace gpb {
 struct OzEx {
   int m = 0, n = 0, k = 0;
   double alpha = 1.0, beta = 0.0;
-  const double* A = nullptr; long lda = 0; int a_tri = 0, a_row0 = 0, a_col0 = 0;
-  const double* B = nullptr; long ldb = 0; int b_tri = 0, b_row0 = 0, b_col0 = 0;
+  // operands: logical A is m x k, logical B is n x k.  *_trans = 0: stored like that (row-major, K-major);
+  // *_trans = 1: stored as the k x m (k x n) row-major array whose transpose is meant (the split transposes on the fly).
+  // *_tri / *_row0 / *_col0 refer to the STORED array: element (r, c) counts as zero when col0 + c lies left of the
+  // 128-block of row0 + r (upper triangular by blocks inside a buffer whose other blocks hold unrelated data).
+  const double* A = nullptr; long lda = 0; int a_trans = 0, a_tri = 0, a_row0 = 0, a_col0 = 0;
+  const double* B = nullptr; long ldb = 0; int b_trans = 0, b_tri = 0, b_row0 = 0, b_col0 = 0;
   double* C = nullptr; long ldc = 0;
   int lower = 0;            // skip 128-blocks right of the diagonal; rows of C are global rows gi0 + i, columns global j
   int gi0 = 0;
