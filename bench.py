@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vendor-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-int8-sliced", action="store_true", help="skip the experimental int8-sliced engine block")
     return ap.parse_args()
 
 
@@ -389,9 +390,10 @@ def one_eval(model):
     return loss
 
 
-def check_parity(n, loss_value, grads):
+def check_parity(n, loss_value, grads, fatal=True):
     """Loss (<= 1e-9) and gradients (<= 1e-7) of the timed evaluation against the unmodified reference's values at the
-    named size; raises if the fast path has drifted -- a fast kernel whose results differ is not done."""
+    named size; raises if the fast path has drifted -- a fast kernel whose results differ is not done.  (fatal=False:
+    report `within_tolerance` instead, used for the experimental int8-sliced engine.)"""
     pin = reference_pin(n)
     if pin is None:
         return {"loss_pin": None, "parity": "no reference pin for N=%d" % n}
@@ -407,7 +409,9 @@ def check_parity(n, loss_value, grads):
         out["loss_pin_" + arm] = ref["loss"]
         out["loss_rel_vs_reference_" + arm] = rel_loss
         out["grad_rel_vs_reference_" + arm] = rel_grad
-        if rel_loss > 1e-9 or rel_grad > 1e-7:
+        if not fatal:
+            out["within_tolerance"] = out.get("within_tolerance", True) and rel_loss <= 1e-9 and rel_grad <= 1e-7
+        elif rel_loss > 1e-9 or rel_grad > 1e-7:
             raise SystemExit("bench.py: PARITY FAILURE against the reference (%s arm): loss rel %.3e, gradient rel %.3e"
                              % (arm, rel_loss, rel_grad))
     out["loss_pin"] = pin["cpu"]["loss"] if "cpu" in pin else pin["cuda"]["loss"]
@@ -473,6 +477,49 @@ def run_ours(args, rank, world, local_rank):
     h2d = (x_host.numel() + y_host.numel()) * 8
     d2h = (host_loss.numel() + sum(g.numel() for g in host_grads)) * 8
 
+    # ---------------- EXPERIMENTAL engine, reported beside the headline (never part of `value`) -----------------
+    int8_sliced = None
+    if world == 1 and not args.no_int8_sliced and n >= 8192:
+        int8_sliced = {"what": "the same loss+grad with the O(N^3) products of gpb_potrf_lower / gpb_potri_lower on the INT8 "
+                               "tensor path: FP64 operands cut into 7-bit slices by this library's split kernel, slice products "
+                               "by cuBLASLt int8 GEMMs (library calls) over a concatenated k, fp64 recombination by this "
+                               "library's kernel (csrc/gpb_ozaki.cu; off by default: GPB_OZAKI / gpb_ozaki_config). Everything "
+                               "else -- and `value`, `e2e`, `roofline` above -- is the hand-written FP64 DMMA path.",
+                       "runs": {}}
+        def grads_now():
+            return {"kernel.variance": model.kernel.variance.grad.cpu().numpy(),
+                    "kernel.length_scales": model.kernel.length_scales.grad.cpu().numpy(),
+                    "likelihood.variance": model.likelihood.variance.grad.cpu().numpy()}
+        try:
+            for slices in (8, 7):
+                nv.ozaki_config(slices)
+                for _ in range(2):
+                    one_eval(model)
+                timer2 = nv.PhaseTimer()
+                nv.install_timer(timer2)
+                torch.cuda.synchronize()
+                k_steps = min(args.steps, 3)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(k_steps):
+                    loss8 = one_eval(model)
+                f1.record()
+                torch.cuda.synchronize()
+                nv.install_timer(None)
+                ms8 = f0.elapsed_time(f1) / k_steps
+                ph8 = timer2.totals_ms()
+                int8_sliced["runs"]["slices_%d" % slices] = {
+                    "ms_per_step": ms8, "evals_per_s": 1000.0 / ms8, "speedup_vs_dmma": (ms / args.steps) / ms8,
+                    "steps": k_steps, "phases_ms_per_step": {k: v / k_steps for k, v in sorted(ph8.items())},
+                    "fp64_equivalent_tflops_potrf_potri": float(n) ** 3 / ((ph8.get("potrf", 0) + ph8.get("potri", 0)) / k_steps) / 1e9,
+                    "loss": float(loss8.item()),
+                    "parity": check_parity(n, float(loss8.item()), grads_now(), fatal=False)}
+        except Exception as exc:    # the experimental engine must never take the bench line down
+            int8_sliced["error"] = "%s: %s" % (type(exc).__name__, exc)
+        finally:
+            nv.install_timer(None)
+            nv.ozaki_config(0)
+
     t = torch.tensor([ms, e2e_sec * 1000.0], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -528,6 +575,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if int8_sliced is not None:
+        line["int8_sliced_experimental"] = int8_sliced
     if sharded is not None:
         line["sharded"] = sharded
     if world == 1 and not args.no_vendor_baseline:

@@ -319,7 +319,23 @@ int ozaki_slices() {
   return s;
 }
 
-void ozaki_set_slices(int s) { g_oz_slices.store((s < 0 || s > OZ_MAX_SLICES) ? 0 : s, std::memory_order_relaxed); }
+void ozaki_set_slices(int s) {
+  s = (s < 0 || s > OZ_MAX_SLICES) ? 0 : s;
+  g_oz_slices.store(s, std::memory_order_relaxed);
+  if (s == 0) {
+    // switching the path off returns its workspaces (several GB at N = 32768) of the current device
+    std::lock_guard<std::mutex> lock(g_oz_mutex);
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    for (auto& kv : g_oz_state) {
+      if (kv.first.first != dev || !kv.second.ws) continue;
+      cudaDeviceSynchronize();
+      cudaFree(kv.second.ws);
+      kv.second.ws = nullptr;
+      kv.second.ws_bytes = 0;
+    }
+  }
+}
 
 int gemm_ozaki_nt(int m, int n, int k, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
                   double* C, long ldc, int lower, int slices, cudaStream_t stream) {
