@@ -749,7 +749,7 @@ int potri_lower(double* A, int n, long lda, const double* dinv, double* kdiag_bl
       x.slices = oz; x.stream = stream;
       rc = gemm_ozaki_nt_ex(x);
     }
-    if (rc != GPB_ERR_UNSUPPORTED) return rc;     // (unsupported can only come from the first strip: nothing written yet)
+    if (rc != GPB_ERR_UNSUPPORTED) return rc;     // (a decline leaves T intact: the DMMA product below recomputes every block)
   }
   GemmArgs g;
   g.M = n; g.N = n; g.K = n;

@@ -427,7 +427,9 @@ int gemm_ozaki_nt_ex(const OzEx& x) {
       const int kk = (u + 1) * k;
       rc = lt_gemm_i8(st, cols, rows, kk, b8 + static_cast<long>(S - 1 - u) * k, ld8, a8 + static_cast<long>(i0) * ld8, ld8,
                       P + static_cast<long>(u) * plane, ldp, lt_ws, stream);
-      if (rc) return rc;
+      // "not taken, use the DMMA engine instead" is only a valid answer while C is untouched: once a strip has been
+      // recombined into C (beta may be 1) a library failure is a hard error, not a fallback
+      if (rc) return (rc == GPB_ERR_UNSUPPORTED && i0 > 0) ? GPB_ERR_DRIVER : rc;
     }
     dim3 grid((cols + 1023) / 1024, rows);
     oz_recombine_kernel<<<grid, 256, 0, stream>>>(P, plane, ldp, S, rows, cols, sa + i0, sb, alpha, beta,
