@@ -320,7 +320,7 @@ int ozaki_slices() {
 }
 
 void ozaki_set_slices(int s) {
-  s = (s < 0 || s > OZ_MAX_SLICES) ? 0 : s;
+  s = (s < 0 || s > OZ_MAX_SLICES) ? 0 : (s == 1 ? 8 : s);     // 1 = "on" = 8 slices, as for GPB_OZAKI
   g_oz_slices.store(s, std::memory_order_relaxed);
   if (s == 0) {
     // switching the path off returns its workspaces (several GB at N = 32768) of the current device
