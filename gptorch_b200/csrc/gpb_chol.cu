@@ -428,7 +428,10 @@ static void panel_schedule(int n, std::vector<int>& starts) {
   // measured on B200 (tools/bench_potrf.py sweeps, profiles/r02_potrf_panel_sweep.txt): narrow panels win while the
   // trailing updates are short (n = 8192: 512 columns 10.7 ms vs 2048 columns 12.7 ms vs plain recursion 13.4 ms), wide
   // panels once the k-length of the trailing GEMMs dominates (n = 32768: 2048 columns 354 ms, 1024 columns 357 ms)
-  const int def = n <= 16384 ? 512 : (n <= 24576 ? 1024 : LA_PANEL);
+  int def = n <= 16384 ? 512 : (n <= 24576 ? 1024 : LA_PANEL);
+  // EXPERIMENTAL int8-sliced engine on: its recombination traffic per update is independent of the panel width, so wide panels
+  // pay earlier (n = 16384, 8 slices: 512 columns 49.6 ms, 1024 columns 43.9 ms, 2048 columns 39.5 ms; n = 32768 flat)
+  if (ozaki_slices() > 0 && n >= 12288) def = LA_PANEL;
   static const int w_env = env_int("GPB_LA_PANEL", 0), first_env = env_int("GPB_LA_FIRST", 0),
                    tail_env = env_int("GPB_LA_TAIL", 0);
   const int w = w_env ? w_env : def, first = first_env ? first_env : w, tail = tail_env ? tail_env : w;
